@@ -439,8 +439,12 @@ struct Basis {
   V3 x, y, z;
 };
 inline Basis basisFromZ(V3 z) { // OrthoNormalBasis.cpp:36-51
-  const V3 helper = std::fabs(z.x) > 0.9999 ? V3{0, 1, 0} : V3{1, 0, 0};
-  const V3 xx = normalised(cross(helper, z));
+  // z.dot(xAxis) is z.x exactly.  The helper-axis cross product written out:
+  // xAxis x z = (0, -z.z, z.y), yAxis x z = (z.z, 0, -z.x) (the reference's generic cross()
+  // yields the same values up to the sign of the zero component, which never survives the
+  // sums it feeds).
+  const V3 c = std::fabs(z.x) > 0.9999 ? V3{z.z, 0.0, -z.x} : V3{0.0, -z.z, z.y};
+  const V3 xx = normalised(c);
   const V3 yy = normalised(cross(z, xx));
   return {xx, yy, z};
 }

@@ -1,0 +1,261 @@
+// Device-side scene layout and the per-ray building blocks shared by every kernel:
+// the brute-force primitive sweep (Scene.cpp:14-122 of the reference), the hit epilogues,
+// camera ray generation and the bounce sampler.
+#pragma once
+
+#include "pt_math.cuh"
+
+namespace ptb200 {
+
+constexpr int kMaxDepth = 64;        // deepest supported RenderParams::maxDepth
+constexpr uint32_t kFullMask = 0xffffffffu;
+
+// ---- layout in HBM --------------------------------------------------------------------------
+// Triangle sweep data is tile-major SoA: tile j holds 9 arrays of `tileTris` doubles
+// (v0x v0y v0z e1x e1y e1z e2x e2y e2z), contiguous, so one TMA bulk copy stages a whole tile
+// into shared memory and a warp that reads triangle i of every array issues 16-byte broadcast
+// loads.  e1 = v1-v0 and e2 = v2-v0 are what TriangleVertices::uVector()/vVector()
+// (TriangleVertices.h:25-31) recompute on every call; storing them is bit-identical.
+// Tiles are padded with all-zero triangles (det == 0 -> skipped, Scene.cpp:66-68).
+struct DeviceScene {
+  const double *triSweep;     // [numTiles][9][tileTris]
+  const double4 *triShade;    // [numTriangles] {shading normal xyz, material index (as double)}
+  const double4 *spheres;     // [numSpheres] {centre xyz, radius^2}   (Sphere.h:7-12)
+  const uint32_t *sphereMaterial;
+  const double *materials;    // [numMaterials][9] MaterialSpec order
+  uint32_t numTriangles;
+  uint32_t numSpheres;
+  uint32_t tileTris;          // triangles per tile (even)
+  uint32_t numTiles;
+  double environment[3];
+};
+
+struct DeviceCamera { // PtCamera / Camera.h:11-18
+  V3 centre, axisX, axisY, axisZ;
+  double aspectRatio, cameraPlaneDist, reciprocalHeight, reciprocalWidth, apertureRadius,
+      focalDistance;
+};
+
+struct Nearest {
+  double t;     // currentNearestDist
+  double det;   // determinant of the winning triangle (for `backfacing`, Scene.cpp:108)
+  int prim;     // INT_MAX-like "none" = kNoPrim; >= 0 triangle; < 0 sphere -(i+1)
+};
+constexpr int kNoPrim = 0x7fffffff;
+
+struct HitInfo {
+  V3 position, normal;
+  uint32_t material;
+  bool inside;
+};
+
+__device__ __forceinline__ double4 ldgDouble4(const double4 *p) {
+  const double2 lo = __ldg(reinterpret_cast<const double2 *>(p));
+  const double2 hi = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+  return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// ---- sphere sweep (Scene.cpp:14-37), spheres in shared memory --------------------------------
+__device__ __forceinline__ void sweepSpheres(const double4 *__restrict__ spheres, int numSpheres,
+                                             V3 o, V3 d, Nearest &best) {
+  for (int i = 0; i < numSpheres; ++i) {
+    const double4 s = spheres[i];
+    const V3 op = sub(mk(s.x, s.y, s.z), o);
+    const double b = dot(op, d);
+    double determinant = fma(b, b, -dot(op, op)) + s.w;
+    if (determinant < 0)
+      continue;
+    determinant = sqrt(determinant);
+    const double minusT = b - determinant;
+    const double plusT = b + determinant;
+    if (minusT < kEpsilon && plusT < kEpsilon)
+      continue;
+    const double t = minusT > kEpsilon ? minusT : plusT;
+    if (t < best.t) {
+      best.t = t;
+      best.prim = -(i + 1);
+    }
+  }
+}
+
+// ---- one ray against one triangle, the reference's Moller-Trumbore (Scene.cpp:62-98) -------
+__device__ __forceinline__ void testTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 d, int index,
+                                             Nearest &best) {
+  const V3 pVec = cross(d, e2);
+  const double det = dot(e1, pVec);
+  const double invDet = 1.0 / det;
+  const V3 tVec = sub(o, v0);
+  const double u = dot(tVec, pVec) * invDet;
+  const V3 qVec = cross(tVec, e1);
+  const double v = dot(d, qVec) * invDet;
+  const double t = dot(e2, qVec) * invDet;
+  // `continue` conditions of Scene.cpp:67,89 and the acceptance test of :94, as one predicate.
+  const bool reject = (fabs(det) < kEpsilon) | (u < 0.0) | (u > 1.0) | (v < 0.0) | (u + v > 1);
+  const bool accept = !reject & (t > kEpsilon) & (t < best.t);
+  if (accept) {
+    best.t = t;
+    best.det = det;
+    best.prim = index;
+  }
+}
+
+// Sweeps triangles [0, count) of a tile that sits in shared memory; `count` is even.
+// Every lane of a warp reads the same addresses (broadcast); two triangles per iteration so
+// each of the 9 arrays is read with one 16-byte load.
+__device__ __forceinline__ void sweepTile(const double *__restrict__ tile, int tileTris, int count,
+                                          int firstIndex, V3 o, V3 d, Nearest &best) {
+#pragma unroll 1
+  for (int i = 0; i < count; i += 2) {
+    const double2 v0x = *reinterpret_cast<const double2 *>(tile + 0 * tileTris + i);
+    const double2 v0y = *reinterpret_cast<const double2 *>(tile + 1 * tileTris + i);
+    const double2 v0z = *reinterpret_cast<const double2 *>(tile + 2 * tileTris + i);
+    const double2 e1x = *reinterpret_cast<const double2 *>(tile + 3 * tileTris + i);
+    const double2 e1y = *reinterpret_cast<const double2 *>(tile + 4 * tileTris + i);
+    const double2 e1z = *reinterpret_cast<const double2 *>(tile + 5 * tileTris + i);
+    const double2 e2x = *reinterpret_cast<const double2 *>(tile + 6 * tileTris + i);
+    const double2 e2y = *reinterpret_cast<const double2 *>(tile + 7 * tileTris + i);
+    const double2 e2z = *reinterpret_cast<const double2 *>(tile + 8 * tileTris + i);
+    testTriangle(mk(v0x.x, v0y.x, v0z.x), mk(e1x.x, e1y.x, e1z.x), mk(e2x.x, e2y.x, e2z.x), o, d,
+                 firstIndex + i, best);
+    testTriangle(mk(v0x.y, v0y.y, v0z.y), mk(e1x.y, e1y.y, e1z.y), mk(e2x.y, e2y.y, e2z.y), o, d,
+                 firstIndex + i + 1, best);
+  }
+}
+
+// ---- hit epilogues (Scene.cpp:38-48 spheres, :99-112 triangles) ------------------------------
+__device__ __forceinline__ HitInfo finishHit(const DeviceScene &scene,
+                                             const double4 *__restrict__ spheres, V3 o, V3 d,
+                                             const Nearest &best) {
+  HitInfo hit;
+  hit.position = positionAlong(o, d, best.t);
+  if (best.prim < 0) {
+    const int i = -best.prim - 1;
+    const double4 s = spheres[i];
+    V3 normal = normalised(sub(hit.position, mk(s.x, s.y, s.z)));
+    hit.inside = dot(normal, d) > 0;
+    hit.normal = hit.inside ? neg(normal) : normal;
+    hit.material = __ldg(scene.sphereMaterial + i);
+  } else {
+    // Three equal vertex normals make Scene.cpp:99-107 independent of u,v; the value is
+    // precomputed at upload (ptb200_shim.cu: shadingNormal()).
+    const double4 sh = ldgDouble4(scene.triShade + best.prim);
+    const bool backfacing = best.det < kEpsilon;
+    hit.inside = backfacing;
+    hit.normal = backfacing ? mk(-sh.x, -sh.y, -sh.z) : mk(sh.x, sh.y, sh.z);
+    hit.material = static_cast<uint32_t>(sh.w);
+  }
+  return hit;
+}
+
+struct MaterialView {
+  const double *m;
+  __device__ __forceinline__ V3 emission() const { return mk(__ldg(m + 0), __ldg(m + 1), __ldg(m + 2)); }
+  __device__ __forceinline__ V3 diffuse() const { return mk(__ldg(m + 3), __ldg(m + 4), __ldg(m + 5)); }
+  __device__ __forceinline__ double indexOfRefraction() const { return __ldg(m + 6); }
+  __device__ __forceinline__ double reflectivity() const { return __ldg(m + 7); }
+  __device__ __forceinline__ double coneAngle() const { return __ldg(m + 8); }
+};
+__device__ __forceinline__ MaterialView materialOf(const DeviceScene &scene, uint32_t index) {
+  return MaterialView{scene.materials + 9 * static_cast<size_t>(index)};
+}
+
+// Reflectivity at a hit (Scene.cpp:140-146).
+__device__ __forceinline__ double hitReflectivity(const MaterialView &mat, const HitInfo &hit,
+                                                  V3 incoming) {
+  const double fixed = mat.reflectivity();
+  if (!(fixed < 0))
+    return fixed;
+  const double ior = mat.indexOfRefraction();
+  return reflectance(hit.normal, incoming, hit.inside ? ior : 1.0, hit.inside ? 1.0 : ior);
+}
+
+// Camera::randomRay + rayFromUnit (Camera.h:20-37,54-60) given its four uniform draws.
+__device__ __forceinline__ void cameraRay(const DeviceCamera &cam, int pixelX, int pixelY,
+                                          double ux, double uy, double uAngle, double uRadius,
+                                          V3 &origin, V3 &direction) {
+  const double x = (pixelX + ux) * cam.reciprocalWidth;
+  const double y = (pixelY + uy) * cam.reciprocalHeight;
+  const double xu = 2 * x - 1;
+  const double yu = 2 * y - 1;
+  const V3 xContrib = scale(scale(cam.axisX, -xu), cam.aspectRatio);
+  const V3 yContrib = scale(cam.axisY, -yu);
+  const V3 zContrib = scale(cam.axisZ, cam.cameraPlaneDist);
+  const V3 dir = normalised(add(add(xContrib, yContrib), zContrib));
+  if (cam.apertureRadius == 0) {
+    origin = cam.centre;
+    direction = dir;
+    return;
+  }
+  const V3 focalPoint = positionAlong(cam.centre, dir, cam.focalDistance);
+  const double angle = uAngle * (2 * kPi);
+  const double radius = uRadius * cam.apertureRadius;
+  double sinA, cosA;
+  sinCos(angle, sinA, cosA);
+  origin = add(add(cam.centre, scale(scale(cam.axisX, cosA), radius)),
+               scale(scale(cam.axisY, sinA), radius));
+  direction = normalised(sub(focalPoint, origin));
+}
+
+// One stratified bounce (Scene.cpp:157-175): returns the new direction and whether the
+// specular branch was taken.  (uSample,vSample) of (numU,numV) strata; (ru,rv,rp) are the
+// three uniform draws in the reference's order.
+__device__ __forceinline__ bool sampleBounce(V3 normal, const Basis &basis, V3 incoming,
+                                             double reflectivity, double coneAngle, int uSample,
+                                             int numU, int vSample, int numV, double ru, double rv,
+                                             double rp, V3 &newDirection) {
+  const double u = (static_cast<double>(uSample) + ru) / static_cast<double>(numU);
+  const double v = (static_cast<double>(vSample) + rv) / static_cast<double>(numV);
+  if (rp < reflectivity) {
+    newDirection = coneSample(reflect(normal, incoming), coneAngle, u, v);
+    return true;
+  }
+  newDirection = hemisphereSample(basis, u, v);
+  return false;
+}
+
+// result += emission + radiance  /  result += emission + diffuse * radiance (Scene.cpp:168,172-174)
+__device__ __forceinline__ V3 shadeTerm(const MaterialView &mat, bool specular, V3 incoming) {
+  const V3 e = mat.emission();
+  if (specular)
+    return add(e, incoming);
+  const V3 k = mat.diffuse();
+  return mk(fma(k.x, incoming.x, e.x), fma(k.y, incoming.y, e.y), fma(k.z, incoming.z, e.z));
+}
+
+// ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UBLKCP, SYNCS) ----------------------------
+__device__ __forceinline__ uint32_t smemAddress(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddress(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddress(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+  asm volatile("{\n"
+               ".reg .pred p;\n"
+               "WAIT_LOOP:\n"
+               "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+               "@p bra WAIT_DONE;\n"
+               "bra WAIT_LOOP;\n"
+               "WAIT_DONE:\n"
+               "}" ::"r"(smemAddress(bar)),
+               "r"(parity)
+               : "memory");
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on `bar`.
+__device__ __forceinline__ void tmaLoad1D(void *dstShared, const void *srcGlobal, uint32_t bytes,
+                                          uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smemAddress(dstShared)),
+               "l"(srcGlobal), "r"(bytes), "r"(smemAddress(bar))
+               : "memory");
+}
+__device__ __forceinline__ void fenceBarrierInit() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+} // namespace ptb200

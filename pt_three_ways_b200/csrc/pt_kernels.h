@@ -1,0 +1,78 @@
+// Argument blocks and host-callable launchers of the sm_100a kernels (pt_kernels.cu).
+#pragma once
+
+#include "pt_device.cuh"
+
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ptb200 {
+
+struct PtPixelDevice { // == PtPixel (include/ptb200.h)
+  double sum[3];
+  unsigned long long numSamples;
+};
+
+struct PtHitDevice { // == PtHit (include/ptb200.h)
+  int32_t hit, inside, material, primitive;
+  double distance;
+  double position[3];
+  double normal[3];
+};
+
+struct KeyedArgs {
+  DeviceScene scene;
+  DeviceCamera camera;
+  uint32_t width;
+  int32_t rowBegin, rowStep;
+  uint32_t ownPixels;              // pixels of the selected rows
+  unsigned long long totalItems;   // ownPixels * passes of this batch
+  int32_t seed, passBegin;         // pass s of the batch uses key seed + passBegin + s
+  int32_t maxDepth, firstBounceU, firstBounceV, preview;
+  double *samples;                 // [passInBatch][ownPixel][3]
+  unsigned long long *ticket;      // work counter, zeroed before launch
+  unsigned long long *castCounter;
+};
+
+struct SequentialArgs {
+  DeviceScene scene;
+  DeviceCamera camera;
+  int32_t width, height;
+  int32_t seed, passBegin, numPasses;
+  int32_t maxDepth, firstBounceU, firstBounceV, preview;
+  double *samples;                 // [passInBatch][height*width][3]
+  unsigned long long *castCounter;
+};
+
+struct ReduceArgs {
+  const double *samples;
+  PtPixelDevice *accumulator;      // full frame
+  uint32_t width;
+  uint32_t rowBegin, rowStep;
+  uint32_t ownPixels;
+  uint32_t numPasses;
+  size_t samplePassStride;         // pixels per pass in `samples`
+  int32_t samplesAreFullFrame;     // sequential kernel writes whole frames
+};
+
+struct IntersectArgs {
+  DeviceScene scene;
+  const double *rays;
+  PtHitDevice *out;
+  uint32_t numRays;
+  int32_t which;                   // 0 intersect, 1 spheres only, 2 triangles only
+  double nearerThan;
+  int32_t warpCooperative;
+};
+
+size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles);
+cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, size_t smemBytes,
+                              cudaStream_t stream, int *blocksLaunched);
+cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream);
+cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream);
+cudaError_t launchIntersect(const IntersectArgs &args, size_t smemBytes, cudaStream_t stream);
+cudaError_t launchFp64Peak(double *sink, int iterations, int blocks, int threads,
+                           cudaStream_t stream);
+
+} // namespace ptb200

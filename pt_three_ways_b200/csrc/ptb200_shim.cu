@@ -1,0 +1,692 @@
+// extern "C" shim: the C ABI of include/ptb200.h on top of the sm_100a kernels.
+//
+// Host-side duties only: validate arguments, build the device scene layout (tile-major SoA,
+// per-triangle shading normal), upload it once, launch kernels on one stream, time them with
+// CUDA events on that stream, and copy the framebuffer back.  No rendering arithmetic runs on
+// the host and there is no CPU fallback: every compute entry point needs a CUDA device.
+#include "ptb200.h"
+
+#include "pt_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+using namespace ptb200;
+
+static_assert(sizeof(PtPixel) == sizeof(PtPixelDevice), "PtPixel layout");
+static_assert(sizeof(PtHit) == sizeof(PtHitDevice), "PtHit layout");
+static_assert(sizeof(PtCamera) == 18 * sizeof(double), "PtCamera layout");
+static_assert(sizeof(DeviceCamera) == sizeof(PtCamera), "DeviceCamera layout");
+static_assert(sizeof(PtMaterial) == 9 * sizeof(double), "PtMaterial layout");
+
+namespace {
+
+thread_local char gLastError[512] = "";
+
+int fail(int code, const char *format, ...) {
+  va_list args;
+  va_start(args, format);
+  vsnprintf(gLastError, sizeof gLastError, format, args);
+  va_end(args);
+  return code;
+}
+
+#define PT_CUDA(call)                                                                            \
+  do {                                                                                           \
+    const cudaError_t ptErr_ = (call);                                                           \
+    if (ptErr_ != cudaSuccess)                                                                   \
+      return fail(PTB200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(ptErr_));             \
+  } while (0)
+
+constexpr size_t kResidentTileBytes = 100 * 1024; // one tile per CTA, two CTAs per SM
+constexpr size_t kStreamTileBytes = 50 * 1024;    // two buffers of this per CTA when streaming
+constexpr size_t kSampleBufferBytes = size_t(4) << 30;
+
+// ---- host restatement of the per-triangle values the reference derives in addTriangle ----
+struct H3 {
+  double x, y, z;
+};
+H3 hsub(H3 a, H3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+double hdot(H3 a, H3 b) { return std::fma(a.z, b.z, std::fma(a.y, b.y, a.x * b.x)); }
+H3 hcross(H3 a, H3 b) {
+  return {std::fma(a.y, b.z, -(a.z * b.y)), std::fma(a.z, b.x, -(a.x * b.z)),
+          std::fma(a.x, b.y, -(a.y * b.x))};
+}
+H3 hnormalised(H3 a) {
+  const double reciprocal = 1.0 / std::sqrt(hdot(a, a));
+  return {a.x * reciprocal, a.y * reciprocal, a.z * reciprocal};
+}
+// Scene::addTriangle stores faceNormal() three times (Scene.cpp:181-187,
+// TriangleVertices.h:33-35); intersectTriangles then evaluates
+// normalised(u*(n1-n0) + v*(n2-n0) + n0) (Scene.cpp:99-107), which for n0==n1==n2 is
+// normalised(0 + n0) whatever u and v are.
+H3 shadingNormal(H3 e1, H3 e2) {
+  const H3 face = hnormalised(hcross(e1, e2));
+  return hnormalised(H3{0.0 + face.x, 0.0 + face.y, 0.0 + face.z});
+}
+
+template <typename T>
+struct DeviceBuffer {
+  T *ptr{nullptr};
+  size_t count{0};
+  ~DeviceBuffer() { release(); }
+  void release() {
+    if (ptr)
+      cudaFree(ptr);
+    ptr = nullptr;
+    count = 0;
+  }
+  cudaError_t ensure(size_t n) {
+    if (n <= count && ptr)
+      return cudaSuccess;
+    release();
+    const cudaError_t err = cudaMalloc(reinterpret_cast<void **>(&ptr), std::max<size_t>(n, 1) * sizeof(T));
+    if (err == cudaSuccess)
+      count = std::max<size_t>(n, 1);
+    return err;
+  }
+};
+
+} // namespace
+
+struct PtContext {
+  int device{0};
+  int numSms{0};
+  cudaStream_t stream{nullptr};
+  bool haveScene{false};
+  DeviceScene scene{};
+  DeviceBuffer<double> triSweep;
+  DeviceBuffer<double4> triShade;
+  DeviceBuffer<double4> spheres;
+  DeviceBuffer<uint32_t> sphereMaterial;
+  DeviceBuffer<double> materials;
+  DeviceBuffer<PtPixelDevice> accumulator;
+  DeviceBuffer<double> samples;
+  DeviceBuffer<unsigned long long> counters; // [0] ticket, [1] casts
+  int accWidth{0}, accHeight{0};
+};
+
+namespace {
+
+int validateScene(const PtScene *scene) {
+  if (!scene)
+    return fail(PTB200_EINVAL, "scene is null");
+  if (scene->numTriangles && (!scene->triangleVertices || !scene->triangleMaterial))
+    return fail(PTB200_EINVAL, "triangle arrays are null");
+  if (scene->numSpheres && (!scene->sphereCentreRadius || !scene->sphereMaterial))
+    return fail(PTB200_EINVAL, "sphere arrays are null");
+  if (!scene->materials || scene->numMaterials == 0)
+    return fail(PTB200_EINVAL, "material palette is empty");
+  if (scene->numMaterials > 65535)
+    return fail(PTB200_EINVAL, "more than 65535 materials");
+  for (uint32_t i = 0; i < scene->numTriangles; ++i)
+    if (scene->triangleMaterial[i] >= scene->numMaterials)
+      return fail(PTB200_EINVAL, "triangle %u: material index out of range", i);
+  for (uint32_t i = 0; i < scene->numSpheres; ++i)
+    if (scene->sphereMaterial[i] >= scene->numMaterials)
+      return fail(PTB200_EINVAL, "sphere %u: material index out of range", i);
+  if (static_cast<size_t>(scene->numSpheres) * 32 > 64 * 1024)
+    return fail(PTB200_EINVAL, "more than 2048 spheres");
+  return PTB200_OK;
+}
+
+int validateParams(const PtRenderParams *p, const PtRenderOptions *o) {
+  if (!p)
+    return fail(PTB200_EINVAL, "params is null");
+  if (p->width <= 0 || p->height <= 0)
+    return fail(PTB200_EINVAL, "image size %dx%d", p->width, p->height);
+  if (p->samplesPerPixel < 0)
+    return fail(PTB200_EINVAL, "negative samplesPerPixel");
+  if (p->maxDepth > kMaxDepth)
+    return fail(PTB200_EINVAL, "maxDepth %d exceeds the supported %d", p->maxDepth, kMaxDepth);
+  if (p->firstBounceUSamples <= 0 || p->firstBounceVSamples <= 0)
+    return fail(PTB200_EINVAL, "first-bounce sample counts must be positive");
+  if (o) {
+    if (o->rngMode != PTB200_RNG_KEYED_PHILOX && o->rngMode != PTB200_RNG_MT19937_SEQUENTIAL)
+      return fail(PTB200_EINVAL, "unknown rngMode %d", o->rngMode);
+    if (o->rowStep < 0 || o->rowBegin < 0)
+      return fail(PTB200_EINVAL, "negative row partition");
+    if (o->rngMode == PTB200_RNG_MT19937_SEQUENTIAL && (o->rowBegin != 0 || o->rowStep > 1))
+      return fail(PTB200_EINVAL,
+                  "the sequential mt19937 stream cannot be partitioned by rows; partition passes");
+  }
+  return PTB200_OK;
+}
+
+void planTiles(uint32_t numTriangles, uint32_t &tileTris, uint32_t &numTiles) {
+  if (numTriangles == 0) {
+    tileTris = 0;
+    numTiles = 0;
+    return;
+  }
+  const size_t bytes = static_cast<size_t>(numTriangles) * 72;
+  numTiles = bytes <= kResidentTileBytes
+                 ? 1u
+                 : static_cast<uint32_t>((bytes + kStreamTileBytes - 1) / kStreamTileBytes);
+  tileTris = (numTriangles + numTiles - 1) / numTiles;
+  tileTris = (tileTris + 1u) & ~1u;
+  numTiles = (numTriangles + tileTris - 1) / tileTris;
+}
+
+DeviceCamera toDeviceCamera(const PtCamera &c) {
+  DeviceCamera d;
+  std::memcpy(&d, &c, sizeof d);
+  return d;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *ptb200_last_error(void) { return gLastError; }
+
+int ptb200_device_count(int32_t *count) {
+  if (!count)
+    return fail(PTB200_EINVAL, "count is null");
+  int n = 0;
+  const cudaError_t err = cudaGetDeviceCount(&n);
+  if (err != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count = n;
+  return PTB200_OK;
+}
+
+int ptb200_context_create(int32_t device, PtContext **out) {
+  if (!out)
+    return fail(PTB200_EINVAL, "out is null");
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(PTB200_ECUDA, "no CUDA device available (this backend has no CPU fallback)");
+  }
+  if (device < 0 || device >= n)
+    return fail(PTB200_EINVAL, "device %d out of range (have %d)", device, n);
+  PT_CUDA(cudaSetDevice(device));
+  auto *ctx = new (std::nothrow) PtContext;
+  if (!ctx)
+    return fail(PTB200_ENOMEM, "out of host memory");
+  ctx->device = device;
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+    delete ctx;
+    return fail(PTB200_ECUDA, "cudaGetDeviceProperties failed");
+  }
+  ctx->numSms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return fail(PTB200_ECUDA, "cudaStreamCreate failed");
+  }
+  if (ctx->counters.ensure(2) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return fail(PTB200_ENOMEM, "device allocation failed");
+  }
+  *out = ctx;
+  return PTB200_OK;
+}
+
+void ptb200_context_destroy(PtContext *ctx) {
+  if (!ctx)
+    return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  delete ctx;
+}
+
+int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
+  if (!ctx)
+    return fail(PTB200_EINVAL, "context is null");
+  if (const int rc = validateScene(scene))
+    return rc;
+  PT_CUDA(cudaSetDevice(ctx->device));
+  DeviceScene d{};
+  d.numTriangles = scene->numTriangles;
+  d.numSpheres = scene->numSpheres;
+  planTiles(scene->numTriangles, d.tileTris, d.numTiles);
+
+  const size_t sweepDoubles = static_cast<size_t>(d.numTiles) * 9 * d.tileTris;
+  std::vector<double> sweep(sweepDoubles, 0.0);
+  std::vector<double4> shade(scene->numTriangles);
+  for (uint32_t i = 0; i < scene->numTriangles; ++i) {
+    const double *t = scene->triangleVertices + 9 * static_cast<size_t>(i);
+    const H3 v0{t[0], t[1], t[2]}, v1{t[3], t[4], t[5]}, v2{t[6], t[7], t[8]};
+    const H3 e1 = hsub(v1, v0), e2 = hsub(v2, v0);
+    const uint32_t tile = i / d.tileTris, within = i % d.tileTris;
+    double *base = sweep.data() + static_cast<size_t>(tile) * 9 * d.tileTris + within;
+    const double values[9] = {v0.x, v0.y, v0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z};
+    for (int a = 0; a < 9; ++a)
+      base[static_cast<size_t>(a) * d.tileTris] = values[a];
+    const H3 n = shadingNormal(e1, e2);
+    shade[i] = make_double4(n.x, n.y, n.z, static_cast<double>(scene->triangleMaterial[i]));
+  }
+  std::vector<double4> spheres(scene->numSpheres);
+  for (uint32_t i = 0; i < scene->numSpheres; ++i) {
+    const double *s = scene->sphereCentreRadius + 4 * static_cast<size_t>(i);
+    spheres[i] = make_double4(s[0], s[1], s[2], s[3] * s[3]); // Sphere.h:11
+  }
+
+  PT_CUDA(ctx->triSweep.ensure(sweepDoubles));
+  PT_CUDA(ctx->triShade.ensure(shade.size()));
+  PT_CUDA(ctx->spheres.ensure(spheres.size()));
+  PT_CUDA(ctx->sphereMaterial.ensure(scene->numSpheres));
+  PT_CUDA(ctx->materials.ensure(static_cast<size_t>(scene->numMaterials) * 9));
+  if (sweepDoubles)
+    PT_CUDA(cudaMemcpyAsync(ctx->triSweep.ptr, sweep.data(), sweepDoubles * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (!shade.empty())
+    PT_CUDA(cudaMemcpyAsync(ctx->triShade.ptr, shade.data(), shade.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (!spheres.empty()) {
+    PT_CUDA(cudaMemcpyAsync(ctx->spheres.ptr, spheres.data(), spheres.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CUDA(cudaMemcpyAsync(ctx->sphereMaterial.ptr, scene->sphereMaterial, scene->numSpheres * 4, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  PT_CUDA(cudaMemcpyAsync(ctx->materials.ptr, scene->materials, static_cast<size_t>(scene->numMaterials) * 72,
+                          cudaMemcpyHostToDevice, ctx->stream));
+  PT_CUDA(cudaStreamSynchronize(ctx->stream)); // staging vectors go out of scope
+  d.triSweep = ctx->triSweep.ptr;
+  d.triShade = ctx->triShade.ptr;
+  d.spheres = ctx->spheres.ptr;
+  d.sphereMaterial = ctx->sphereMaterial.ptr;
+  d.materials = ctx->materials.ptr;
+  d.environment[0] = scene->environment[0];
+  d.environment[1] = scene->environment[1];
+  d.environment[2] = scene->environment[2];
+  ctx->scene = d;
+  ctx->haveScene = true;
+  return PTB200_OK;
+}
+
+// Launches the batches of one render call on ctx->stream; does not synchronise.
+static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderParams *params,
+                         const PtRenderOptions *options, int passBegin, int numPasses,
+                         std::vector<cudaEvent_t> *events, uint64_t *launches) {
+  const PtRenderOptions defaults{};
+  const PtRenderOptions &opt = options ? *options : defaults;
+  const int rowStep = opt.rowStep > 0 ? opt.rowStep : 1;
+  const int rowBegin = opt.rowBegin;
+  const uint32_t ownRows = rowBegin >= params->height
+                               ? 0u
+                               : static_cast<uint32_t>((params->height - rowBegin + rowStep - 1) / rowStep);
+  const uint32_t ownPixels = ownRows * static_cast<uint32_t>(params->width);
+  if (ownPixels == 0 || numPasses == 0)
+    return PTB200_OK;
+  const bool sequential = opt.rngMode == PTB200_RNG_MT19937_SEQUENTIAL;
+  const size_t pixelsPerPass = sequential ? static_cast<size_t>(params->width) * params->height : ownPixels;
+  size_t passesPerBatch = std::max<size_t>(1, kSampleBufferBytes / (pixelsPerPass * 24));
+  if (opt.passesPerBatch > 0)
+    passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(opt.passesPerBatch));
+  passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses));
+  PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
+
+  for (int done = 0; done < numPasses;) {
+    const int batch = static_cast<int>(std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses - done)));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (events) {
+      PT_CUDA(cudaEventCreate(&e0));
+      PT_CUDA(cudaEventCreate(&e1));
+      PT_CUDA(cudaEventRecord(e0, ctx->stream));
+    }
+    if (sequential) {
+      SequentialArgs a{};
+      a.scene = ctx->scene;
+      a.camera = toDeviceCamera(*camera);
+      a.width = params->width;
+      a.height = params->height;
+      a.seed = params->seed;
+      a.passBegin = passBegin + done;
+      a.numPasses = batch;
+      a.maxDepth = params->maxDepth;
+      a.firstBounceU = params->firstBounceUSamples;
+      a.firstBounceV = params->firstBounceVSamples;
+      a.preview = params->preview;
+      a.samples = ctx->samples.ptr;
+      a.castCounter = ctx->counters.ptr + 1;
+      PT_CUDA(launchRenderSequential(a, ctx->stream));
+    } else {
+      PT_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(unsigned long long), ctx->stream));
+      KeyedArgs a{};
+      a.scene = ctx->scene;
+      a.camera = toDeviceCamera(*camera);
+      a.width = static_cast<uint32_t>(params->width);
+      a.rowBegin = rowBegin;
+      a.rowStep = rowStep;
+      a.ownPixels = ownPixels;
+      a.totalItems = static_cast<unsigned long long>(ownPixels) * static_cast<unsigned long long>(batch);
+      a.seed = params->seed;
+      a.passBegin = passBegin + done;
+      a.maxDepth = params->maxDepth;
+      a.firstBounceU = params->firstBounceUSamples;
+      a.firstBounceV = params->firstBounceVSamples;
+      a.preview = params->preview;
+      a.samples = ctx->samples.ptr;
+      a.ticket = ctx->counters.ptr;
+      a.castCounter = ctx->counters.ptr + 1;
+      const size_t smem = keyedSmemBytes(ctx->scene.numSpheres, ctx->scene.tileTris, ctx->scene.numTiles);
+      PT_CUDA(launchRenderKeyed(a, ctx->numSms, smem, ctx->stream, nullptr));
+    }
+    if (events) {
+      PT_CUDA(cudaEventRecord(e1, ctx->stream));
+      events->push_back(e0);
+      events->push_back(e1);
+    }
+    ReduceArgs r{};
+    r.samples = ctx->samples.ptr;
+    r.accumulator = ctx->accumulator.ptr;
+    r.width = static_cast<uint32_t>(params->width);
+    r.rowBegin = static_cast<uint32_t>(rowBegin);
+    r.rowStep = static_cast<uint32_t>(rowStep);
+    r.ownPixels = ownPixels;
+    r.numPasses = static_cast<uint32_t>(batch);
+    r.samplePassStride = pixelsPerPass;
+    r.samplesAreFullFrame = sequential ? 1 : 0;
+    PT_CUDA(launchReducePasses(r, ctx->stream));
+    if (launches)
+      *launches += 2;
+    done += batch;
+  }
+  return PTB200_OK;
+}
+
+int ptb200_context_render(PtContext *ctx, const PtCamera *camera, const PtRenderParams *params,
+                          const PtRenderOptions *options, int32_t accumulate, PtStats *stats) {
+  if (!ctx || !camera)
+    return fail(PTB200_EINVAL, "null argument");
+  if (const int rc = validateParams(params, options))
+    return rc;
+  if (!ctx->haveScene)
+    return fail(PTB200_ESTATE, "no scene uploaded");
+  PT_CUDA(cudaSetDevice(ctx->device));
+  const size_t pixels = static_cast<size_t>(params->width) * params->height;
+  const bool sameSize = ctx->accWidth == params->width && ctx->accHeight == params->height;
+  PT_CUDA(ctx->accumulator.ensure(pixels));
+  if (!accumulate || !sameSize)
+    PT_CUDA(cudaMemsetAsync(ctx->accumulator.ptr, 0, pixels * sizeof(PtPixelDevice), ctx->stream));
+  ctx->accWidth = params->width;
+  ctx->accHeight = params->height;
+  PT_CUDA(cudaMemsetAsync(ctx->counters.ptr + 1, 0, sizeof(unsigned long long), ctx->stream));
+
+  cudaEvent_t begin = nullptr, end = nullptr;
+  PT_CUDA(cudaEventCreate(&begin));
+  PT_CUDA(cudaEventCreate(&end));
+  std::vector<cudaEvent_t> events;
+  uint64_t launches = 0;
+  PT_CUDA(cudaEventRecord(begin, ctx->stream));
+  const int rc = enqueueRender(ctx, camera, params, options, options ? options->passBegin : 0,
+                               params->samplesPerPixel, &events, &launches);
+  if (rc == PTB200_OK) {
+    PT_CUDA(cudaEventRecord(end, ctx->stream));
+    PT_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (rc == PTB200_OK && stats) {
+    float ms = 0;
+    PT_CUDA(cudaEventElapsedTime(&ms, begin, end));
+    double sweepMs = 0;
+    for (size_t i = 0; i + 1 < events.size(); i += 2) {
+      float part = 0;
+      PT_CUDA(cudaEventElapsedTime(&part, events[i], events[i + 1]));
+      sweepMs += part;
+    }
+    unsigned long long casts = 0;
+    PT_CUDA(cudaMemcpy(&casts, ctx->counters.ptr + 1, sizeof casts, cudaMemcpyDeviceToHost));
+    const PtRenderOptions defaults{};
+    const PtRenderOptions &opt = options ? *options : defaults;
+    const int rowStep = opt.rowStep > 0 ? opt.rowStep : 1;
+    const uint64_t ownRows = opt.rowBegin >= params->height
+                                 ? 0
+                                 : static_cast<uint64_t>((params->height - opt.rowBegin + rowStep - 1) / rowStep);
+    stats->samples = ownRows * static_cast<uint64_t>(params->width) * static_cast<uint64_t>(params->samplesPerPixel);
+    stats->casts = casts;
+    stats->kernelLaunches = launches;
+    stats->kernelMs = ms;
+    stats->sweepKernelMs = sweepMs;
+  }
+  for (cudaEvent_t e : events)
+    cudaEventDestroy(e);
+  cudaEventDestroy(begin);
+  cudaEventDestroy(end);
+  return rc;
+}
+
+int ptb200_context_download(PtContext *ctx, PtPixel *out) {
+  if (!ctx || !out)
+    return fail(PTB200_EINVAL, "null argument");
+  if (!ctx->accumulator.ptr || ctx->accWidth == 0)
+    return fail(PTB200_ESTATE, "nothing rendered yet");
+  PT_CUDA(cudaSetDevice(ctx->device));
+  const size_t pixels = static_cast<size_t>(ctx->accWidth) * ctx->accHeight;
+  PT_CUDA(cudaMemcpyAsync(out, ctx->accumulator.ptr, pixels * sizeof(PtPixel), cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PTB200_OK;
+}
+
+int ptb200_render(const PtScene *scene, const PtCamera *camera, const PtRenderParams *params,
+                  const PtRenderOptions *options, PtPixel *out, PtProgressFn progress, void *user,
+                  PtStats *stats) {
+  if (!camera || !out)
+    return fail(PTB200_EINVAL, "null argument");
+  if (const int rc = validateParams(params, options))
+    return rc;
+  PtContext *ctx = nullptr;
+  int rc = ptb200_context_create(options ? options->device : 0, &ctx);
+  if (rc)
+    return rc;
+  rc = ptb200_context_upload_scene(ctx, scene);
+  PtStats total{};
+  if (rc == PTB200_OK) {
+    if (!progress) {
+      rc = ptb200_context_render(ctx, camera, params, options, 0, &total);
+    } else {
+      // Progressive: render in slices of passes, handing the partial framebuffer to the
+      // caller on this thread between slices (Scene.cpp:242-245 does so per collected pass).
+      PtRenderOptions slice = options ? *options : PtRenderOptions{};
+      const int spp = params->samplesPerPixel;
+      const int step = slice.passesPerBatch > 0 ? slice.passesPerBatch : std::max(1, (spp + 19) / 20);
+      const int firstPass = slice.passBegin;
+      for (int done = 0; done < spp && rc == PTB200_OK;) {
+        PtRenderParams part = *params;
+        part.samplesPerPixel = std::min(step, spp - done);
+        slice.passBegin = firstPass + done;
+        PtStats one{};
+        rc = ptb200_context_render(ctx, camera, &part, &slice, done > 0, &one);
+        if (rc)
+          break;
+        total.samples += one.samples;
+        total.casts += one.casts;
+        total.kernelLaunches += one.kernelLaunches;
+        total.kernelMs += one.kernelMs;
+        total.sweepKernelMs += one.sweepKernelMs;
+        done += part.samplesPerPixel;
+        rc = ptb200_context_download(ctx, out);
+        if (rc == PTB200_OK && progress(user, out, done, spp) != 0)
+          break;
+      }
+    }
+  }
+  if (rc == PTB200_OK)
+    rc = ptb200_context_download(ctx, out);
+  ptb200_context_destroy(ctx);
+  if (rc == PTB200_OK && stats)
+    *stats = total;
+  return rc;
+}
+
+int ptb200_render_multi(const PtScene *scene, const PtCamera *camera, const PtRenderParams *params,
+                        const PtRenderOptions *options, const int32_t *devices, int32_t numDevices,
+                        PtPixel *out, PtStats *stats) {
+  if (!camera || !out)
+    return fail(PTB200_EINVAL, "null argument");
+  if (const int rc = validateParams(params, options))
+    return rc;
+  std::vector<int32_t> list;
+  if (devices && numDevices > 0) {
+    list.assign(devices, devices + numDevices);
+  } else {
+    int32_t n = 0;
+    ptb200_device_count(&n);
+    for (int32_t i = 0; i < n; ++i)
+      list.push_back(i);
+  }
+  if (list.empty())
+    return fail(PTB200_ECUDA, "no CUDA device available (this backend has no CPU fallback)");
+  const PtRenderOptions base = options ? *options : PtRenderOptions{};
+  if (base.rowStep > 1 || base.rowBegin != 0)
+    return fail(PTB200_EINVAL, "render_multi partitions rows itself; leave rowBegin/rowStep zero");
+  const int n = static_cast<int>(list.size());
+  const size_t pixels = static_cast<size_t>(params->width) * params->height;
+  const bool sequential = base.rngMode == PTB200_RNG_MT19937_SEQUENTIAL;
+
+  struct Part {
+    std::vector<PtPixel> pixels;
+    PtStats stats{};
+    int rc{PTB200_OK};
+    char error[512]{};
+  };
+  std::vector<Part> parts(n);
+  std::vector<std::thread> threads;
+  for (int g = 0; g < n; ++g) {
+    threads.emplace_back([&, g] {
+      Part &part = parts[g];
+      part.pixels.assign(pixels, PtPixel{});
+      PtRenderOptions opt = base;
+      PtRenderParams prm = *params;
+      opt.device = list[g];
+      if (sequential) { // passes s with s % n == g, as contiguous blocks
+        const int spp = params->samplesPerPixel;
+        const int lo = static_cast<int>(static_cast<long long>(spp) * g / n);
+        const int hi = static_cast<int>(static_cast<long long>(spp) * (g + 1) / n);
+        opt.passBegin = base.passBegin + lo;
+        prm.samplesPerPixel = hi - lo;
+      } else { // rows y with y % n == g
+        opt.rowBegin = g;
+        opt.rowStep = n;
+      }
+      part.rc = ptb200_render(scene, camera, &prm, &opt, part.pixels.data(), nullptr, nullptr, &part.stats);
+      if (part.rc)
+        snprintf(part.error, sizeof part.error, "%s", ptb200_last_error());
+    });
+  }
+  for (auto &t : threads)
+    t.join();
+  PtStats total{};
+  for (int g = 0; g < n; ++g) {
+    if (parts[g].rc)
+      return fail(parts[g].rc, "device %d: %s", list[g], parts[g].error);
+    total.samples += parts[g].stats.samples;
+    total.casts += parts[g].stats.casts;
+    total.kernelLaunches += parts[g].stats.kernelLaunches;
+    total.kernelMs = std::max(total.kernelMs, parts[g].stats.kernelMs);
+    total.sweepKernelMs = std::max(total.sweepKernelMs, parts[g].stats.sweepKernelMs);
+  }
+  // Host-side gather: device order, i.e. for sequential mode ascending pass blocks (the same
+  // operator+= the reference applies to per-pass outputs, ArrayOutput.cpp:48-56).
+  std::memset(out, 0, pixels * sizeof(PtPixel));
+  for (int g = 0; g < n; ++g) {
+    for (size_t i = 0; i < pixels; ++i) {
+      out[i].sum[0] += parts[g].pixels[i].sum[0];
+      out[i].sum[1] += parts[g].pixels[i].sum[1];
+      out[i].sum[2] += parts[g].pixels[i].sum[2];
+      out[i].numSamples += parts[g].pixels[i].numSamples;
+    }
+  }
+  if (stats)
+    *stats = total;
+  return PTB200_OK;
+}
+
+int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double nearerThan,
+                     uint32_t numRays, const double *rays, PtHit *out) {
+  if (numRays == 0)
+    return PTB200_OK;
+  if (!rays || !out)
+    return fail(PTB200_EINVAL, "null argument");
+  // bit 8 of `which` selects the warp-cooperative sweep of the sequential kernel (tests).
+  const int32_t mode = which & 0xff;
+  if (mode < 0 || mode > 2)
+    return fail(PTB200_EINVAL, "which must be 0, 1 or 2");
+  PtContext *ctx = nullptr;
+  int rc = ptb200_context_create(device, &ctx);
+  if (rc)
+    return rc;
+  rc = ptb200_context_upload_scene(ctx, scene);
+  if (rc) {
+    ptb200_context_destroy(ctx);
+    return rc;
+  }
+  DeviceBuffer<double> dRays;
+  DeviceBuffer<PtHitDevice> dOut;
+  auto body = [&]() -> int {
+    PT_CUDA(dRays.ensure(static_cast<size_t>(numRays) * 6));
+    PT_CUDA(dOut.ensure(numRays));
+    PT_CUDA(cudaMemcpyAsync(dRays.ptr, rays, static_cast<size_t>(numRays) * 48, cudaMemcpyHostToDevice, ctx->stream));
+    IntersectArgs a{};
+    a.scene = ctx->scene;
+    a.rays = dRays.ptr;
+    a.out = dOut.ptr;
+    a.numRays = numRays;
+    a.which = mode;
+    a.nearerThan = nearerThan;
+    a.warpCooperative = (which & 0x100) ? 1 : 0;
+    const size_t smem = keyedSmemBytes(ctx->scene.numSpheres, ctx->scene.tileTris, ctx->scene.numTiles);
+    PT_CUDA(launchIntersect(a, smem, ctx->stream));
+    PT_CUDA(cudaMemcpyAsync(out, dOut.ptr, static_cast<size_t>(numRays) * sizeof(PtHit), cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PTB200_OK;
+  };
+  rc = body();
+  dRays.release();
+  dOut.release();
+  ptb200_context_destroy(ctx);
+  return rc;
+}
+
+int ptb200_measure_fp64_peak(int32_t device, double *tflops, double *milliseconds) {
+  if (!tflops)
+    return fail(PTB200_EINVAL, "null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(PTB200_ECUDA, "no CUDA device available");
+  }
+  PT_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  PT_CUDA(cudaGetDeviceProperties(&prop, device));
+  DeviceBuffer<double> sink;
+  PT_CUDA(sink.ensure(1));
+  const int threads = 512, blocks = prop.multiProcessorCount * 4, iterations = 4096;
+  cudaEvent_t e0, e1;
+  PT_CUDA(cudaEventCreate(&e0));
+  PT_CUDA(cudaEventCreate(&e1));
+  double best = 0, bestMs = 0;
+  for (int rep = 0; rep < 5; ++rep) { // first repetitions warm up
+    PT_CUDA(cudaEventRecord(e0, nullptr));
+    PT_CUDA(launchFp64Peak(sink.ptr, iterations, blocks, threads, nullptr));
+    PT_CUDA(cudaEventRecord(e1, nullptr));
+    PT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    PT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8 * 16 * static_cast<double>(iterations) * threads * blocks;
+    const double rate = flops / (ms * 1e-3) / 1e12;
+    if (rate > best) {
+      best = rate;
+      bestMs = ms;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  if (milliseconds)
+    *milliseconds = bestMs;
+  return PTB200_OK;
+}
+
+} // extern "C"
