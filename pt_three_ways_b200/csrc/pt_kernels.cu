@@ -13,6 +13,8 @@
 
 #include "pt_device.cuh"
 
+#include <cstdlib>
+
 namespace ptb200 {
 
 // =============================================================================================
@@ -678,32 +680,50 @@ __global__ void fp64PeakKernel(double *sink, int iterations) {
 // =============================================================================================
 // Host-side launchers (called from ptb200_shim.cu).
 // =============================================================================================
-constexpr int kKeyedBlock = 256;
-constexpr int kKeyedMinBlocks = 2;
 constexpr int kSequentialWarps = 2;
 
-cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, size_t smemBytes, cudaStream_t stream,
+template <int kBlock, int kMinBlocks>
+cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, size_t smemBytes, cudaStream_t stream,
                               int *blocksLaunched) {
-  auto kernel = renderKeyedKernel<kKeyedBlock, kKeyedMinBlocks>;
+  auto kernel = renderKeyedKernel<kBlock, kMinBlocks>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smemBytes));
   if (err != cudaSuccess)
     return err;
   int perSm = 0;
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kKeyedBlock, smemBytes);
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlock, smemBytes);
   if (err != cudaSuccess)
     return err;
   if (perSm < 1)
     return cudaErrorInvalidConfiguration;
-  // Persistent grid: every SM holds `perSm` CTAs for the whole launch.
-  unsigned long long wanted = (args.totalItems + kKeyedBlock - 1) / kKeyedBlock;
+  // Persistent grid: every SM holds `perSm` CTAs for the whole launch (148 x perSm on B200).
+  unsigned long long wanted = (args.totalItems + kBlock - 1) / kBlock;
   unsigned long long grid = static_cast<unsigned long long>(numSms) * perSm;
   if (wanted < grid)
     grid = wanted ? wanted : 1;
   if (blocksLaunched)
     *blocksLaunched = static_cast<int>(grid);
-  kernel<<<static_cast<unsigned>(grid), kKeyedBlock, smemBytes, stream>>>(args);
+  kernel<<<static_cast<unsigned>(grid), kBlock, smemBytes, stream>>>(args);
   return cudaGetLastError();
+}
+
+cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, size_t smemBytes, cudaStream_t stream,
+                              int *blocksLaunched) {
+  // PTB200_KEYED_CONFIG selects a (threads per CTA, min CTAs per SM) pair, i.e. a register
+  // budget; used by tools/sweep_configs.py.  The default is what measured best on B200.
+  static const int config = [] {
+    const char *env = getenv("PTB200_KEYED_CONFIG");
+    return env ? atoi(env) : 0;
+  }();
+  switch (config) {
+  case 1: return launchKeyedConfig<384, 1>(args, numSms, smemBytes, stream, blocksLaunched); // 168 regs
+  case 2: return launchKeyedConfig<512, 1>(args, numSms, smemBytes, stream, blocksLaunched); // 128 regs
+  case 3: return launchKeyedConfig<256, 1>(args, numSms, smemBytes, stream, blocksLaunched); // 255 regs
+  case 4: return launchKeyedConfig<128, 3>(args, numSms, smemBytes, stream, blocksLaunched); // 168 regs
+  case 5: return launchKeyedConfig<128, 5>(args, numSms, smemBytes, stream, blocksLaunched); // 96 regs
+  case 6: return launchKeyedConfig<256, 3>(args, numSms, smemBytes, stream, blocksLaunched); // 80 regs
+  default: return launchKeyedConfig<256, 2>(args, numSms, smemBytes, stream, blocksLaunched); // 128 regs
+  }
 }
 
 cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream) {

@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -178,6 +179,30 @@ DeviceCamera toDeviceCamera(const PtCamera &c) {
   DeviceCamera d;
   std::memcpy(&d, &c, sizeof d);
   return d;
+}
+
+
+
+// One idle context per device is kept between one-shot calls so that repeated ptb200_render()
+// calls reuse the stream and the device allocations (the scene is still uploaded every call).
+std::mutex gPoolMutex;
+std::vector<PtContext *> gPool;
+
+PtContext *poolTake(int device) {
+  std::lock_guard<std::mutex> lock(gPoolMutex);
+  for (size_t i = 0; i < gPool.size(); ++i) {
+    if (gPool[i]->device == device) {
+      PtContext *ctx = gPool[i];
+      gPool.erase(gPool.begin() + static_cast<long>(i));
+      return ctx;
+    }
+  }
+  return nullptr;
+}
+
+void poolGive(PtContext *ctx) {
+  std::lock_guard<std::mutex> lock(gPoolMutex);
+  gPool.push_back(ctx);
 }
 
 } // namespace
@@ -476,10 +501,14 @@ int ptb200_render(const PtScene *scene, const PtCamera *camera, const PtRenderPa
     return fail(PTB200_EINVAL, "null argument");
   if (const int rc = validateParams(params, options))
     return rc;
-  PtContext *ctx = nullptr;
-  int rc = ptb200_context_create(options ? options->device : 0, &ctx);
-  if (rc)
-    return rc;
+  const int device = options ? options->device : 0;
+  PtContext *ctx = poolTake(device);
+  int rc = PTB200_OK;
+  if (!ctx) {
+    rc = ptb200_context_create(device, &ctx);
+    if (rc)
+      return rc;
+  }
   rc = ptb200_context_upload_scene(ctx, scene);
   PtStats total{};
   if (rc == PTB200_OK) {
@@ -514,7 +543,10 @@ int ptb200_render(const PtScene *scene, const PtCamera *camera, const PtRenderPa
   }
   if (rc == PTB200_OK)
     rc = ptb200_context_download(ctx, out);
-  ptb200_context_destroy(ctx);
+  if (rc == PTB200_OK)
+    poolGive(ctx);
+  else
+    ptb200_context_destroy(ctx);
   if (rc == PTB200_OK && stats)
     *stats = total;
   return rc;

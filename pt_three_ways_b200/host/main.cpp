@@ -1,0 +1,158 @@
+// pt_b200 — command-line driver with the reference CLI's flags (src/main/main.cpp:382-404):
+//   -w/--width -h/--height --max-cpus --spp --first-bounce-u --first-bounce-v --max-depth
+//   --seed --preview --save-every --way --scene --raw <output>
+// plus backend flags:  --rng keyed|exact   --gpus N (0 = all)   --scenes DIR   --device K.
+// Scene building, OBJ/MTL loading, the framebuffer and the PNG/raw writers are host C++ here
+// as they are in the reference; render() goes to the GPU through the C ABI.
+#include "ArrayOutput.h"
+#include "HostApi.h"
+#include "PngWriter.h"
+#include "Scene.h"
+#include "SceneRecipes.h"
+
+#include <chrono>
+#include <cstdlib>
+#include <functional>
+#include <iostream>
+#include <random>
+#include <string>
+
+using namespace ptb200;
+
+namespace {
+
+void savePng(const ArrayOutput &output, const std::string &name) {
+  PngWriter pw(name.c_str(), output.width(), output.height());
+  if (!pw.ok()) {
+    std::cerr << "Unable to save PNG\n";
+    return;
+  }
+  std::vector<std::uint8_t> row(static_cast<size_t>(output.width()) * 3);
+  for (int y = 0; y < output.height(); ++y) {
+    for (int x = 0; x < output.width(); ++x) {
+      const auto colour = output.pixelAt(x, y);
+      for (int c = 0; c < 3; ++c)
+        row[static_cast<size_t>(x) * 3 + c] = colour[static_cast<size_t>(c)];
+    }
+    pw.addRow(row.data());
+  }
+}
+
+int usage(const char *argv0) {
+  std::cerr << "usage: " << argv0
+            << " [-w W] [-h H] [--spp N] [--max-cpus N] [--first-bounce-u N] [--first-bounce-v N]\n"
+               "       [--max-depth N] [--seed N] [--preview] [--save-every SECS] [--way dod]\n"
+               "       [--scene NAME] [--raw] [--rng keyed|exact] [--gpus N] [--device K]\n"
+               "       [--scenes DIR] <output>\n";
+  return 1;
+}
+
+} // namespace
+
+int main(int argc, const char *argv[]) {
+  RenderParams renderParams;
+  bool raw = false;
+  int saveEvery = 30;
+  int gpus = 1;
+  int device = 0;
+  std::string way = "dod";
+  std::string sceneName = "cornell";
+  std::string scenesDir = "scenes";
+  std::string rng = "keyed";
+  std::string outputName;
+
+  for (int i = 1; i < argc; ++i) {
+    const std::string arg = argv[i];
+    auto value = [&]() -> std::string {
+      if (i + 1 >= argc) {
+        std::cerr << "Error in command line: missing value for " << arg << '\n';
+        std::exit(1);
+      }
+      return argv[++i];
+    };
+    if (arg == "-w" || arg == "--width") renderParams.width = std::stoi(value());
+    else if (arg == "-h" || arg == "--height") renderParams.height = std::stoi(value());
+    else if (arg == "--max-cpus") renderParams.maxCpus = std::stoi(value());
+    else if (arg == "--spp") renderParams.samplesPerPixel = std::stoi(value());
+    else if (arg == "--first-bounce-u") renderParams.firstBounceUSamples = std::stoi(value());
+    else if (arg == "--first-bounce-v") renderParams.firstBounceVSamples = std::stoi(value());
+    else if (arg == "--max-depth") renderParams.maxDepth = std::stoi(value());
+    else if (arg == "--seed") renderParams.seed = std::stoi(value());
+    else if (arg == "--preview") renderParams.preview = true;
+    else if (arg == "--save-every") saveEvery = std::stoi(value());
+    else if (arg == "--way") way = value();
+    else if (arg == "--scene") sceneName = value();
+    else if (arg == "--raw") raw = true;
+    else if (arg == "--rng") rng = value();
+    else if (arg == "--gpus") gpus = std::stoi(value());
+    else if (arg == "--device") device = std::stoi(value());
+    else if (arg == "--scenes") scenesDir = value();
+    else if (arg == "--help" || arg == "-?") return usage(argv[0]);
+    else if (!arg.empty() && arg[0] == '-') {
+      std::cerr << "Error in command line: unknown option " << arg << '\n';
+      return 1;
+    } else outputName = arg;
+  }
+  if (outputName.empty()) {
+    std::cerr << "Missing output filename.\n";
+    return usage(argv[0]);
+  }
+  if (way != "dod" && way != "b200") {
+    std::cerr << "Unknown way " << way << " (this backend replaces the dod renderer only)\n";
+    return 1;
+  }
+  if (renderParams.seed == 0) { // main.cpp:426-429
+    std::random_device rd;
+    renderParams.seed = static_cast<int>(rd());
+  }
+
+  std::function<void(const ArrayOutput &)> save;
+  if (raw)
+    save = [outputName](const ArrayOutput &output) { output.save(outputName); };
+  else
+    save = [outputName](const ArrayOutput &output) { savePng(output, outputName); };
+
+  try {
+    using namespace std::chrono_literals;
+    const auto every = std::chrono::seconds(saveEvery);
+    auto nextSave = std::chrono::system_clock::now() + every;
+    auto throttledSave = [&](ArrayOutput &output) { // main.cpp:331-343
+      if (every == 0s)
+        return;
+      const auto now = std::chrono::system_clock::now();
+      if (now > nextSave) {
+        save(output);
+        nextSave = now + every;
+      }
+    };
+
+    HostApi api(scenesDir);
+    Scene scene;
+    Camera camera = SceneRecipes<HostApi>::create(api, scene, sceneName, renderParams.width,
+                                                  renderParams.height);
+    std::cout << "Scene contains " << scene.numTriangles() << " triangles and "
+              << scene.numSpheres() << " spheres.\n"; // main.cpp:320-323
+    scene.setRngMode(rng == "exact" ? PTB200_RNG_MT19937_SEQUENTIAL : PTB200_RNG_KEYED_PHILOX);
+    scene.setDevice(device);
+    scene.setUseAllDevices(gpus != 1);
+
+    const auto start = std::chrono::system_clock::now();
+    ArrayOutput output = scene.render(camera, renderParams, throttledSave);
+    const auto end = std::chrono::system_clock::now();
+    save(output);
+
+    const auto taken = end - start;
+    const auto totalSamples = output.totalSamples();
+    const auto ms = std::chrono::duration_cast<std::chrono::milliseconds>(taken).count();
+    std::cout << "Took " << std::chrono::duration_cast<std::chrono::seconds>(taken).count() << "s\n";
+    std::cout << "Total samples: " << totalSamples << "\n";
+    std::cout << "Samples/ms: " << static_cast<double>(totalSamples) / static_cast<double>(ms ? ms : 1)
+              << "\n"; // main.cpp:464-473
+    const PtStats &stats = scene.lastStats();
+    std::cout << "GPU: " << stats.casts << " ray casts, " << stats.kernelMs << " ms in kernels\n";
+  } catch (const std::exception &e) {
+    std::cerr << "Error: " << e.what() << '\n';
+    return 1;
+  }
+  return 0;
+}
