@@ -40,7 +40,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WIDTH, HEIGHT, SPP, SEED = 640, 480, 256, 1
+WIDTH, HEIGHT, SPP, SEED = 640, 480, int(os.environ.get("BENCH_SPP", "256")), 1  # BENCH_SPP: profiling only
 SCENE = "cornell"
 METRIC = "Msamples/sec on CornellBox 640x480"
 UNIT = "Msamples/s"

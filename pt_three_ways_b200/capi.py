@@ -184,11 +184,13 @@ def render(scene, camera18, params: PtRenderParams, options: PtRenderOptions | N
     return out, _stats_dict(st)
 
 
-def intersect(scene, rays, which=0, nearer_than=float("inf"), device=0, warp_cooperative=False):
+def intersect(scene, rays, which=0, nearer_than=float("inf"), device=0, warp_cooperative=False,
+              one_stage=False):
     m = scene if isinstance(scene, MarshalledScene) else MarshalledScene(scene)
     rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
     out = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
-    _check(lib().ptb200_intersect(C.byref(m.abi), device, which | (0x100 if warp_cooperative else 0),
+    flags = (0x100 if warp_cooperative else 0) | (0x200 if one_stage else 0)
+    _check(lib().ptb200_intersect(C.byref(m.abi), device, which | flags,
                                   nearer_than, rays.shape[0], rays.ctypes.data, out.ctypes.data))
     return out
 

@@ -58,6 +58,7 @@ __device__ __forceinline__ double4 ldgDouble4(const double4 *p) {
 // ---- sphere sweep (Scene.cpp:14-37), spheres in shared memory --------------------------------
 __device__ __forceinline__ void sweepSpheres(const double4 *__restrict__ spheres, int numSpheres,
                                              V3 o, V3 d, Nearest &best) {
+#pragma unroll 1
   for (int i = 0; i < numSpheres; ++i) {
     const double4 s = spheres[i];
     const V3 op = sub(mk(s.x, s.y, s.z), o);
@@ -65,7 +66,7 @@ __device__ __forceinline__ void sweepSpheres(const double4 *__restrict__ spheres
     double determinant = fma(b, b, -dot(op, op)) + s.w;
     if (determinant < 0)
       continue;
-    determinant = sqrt(determinant);
+    determinant = ieeeSqrt(determinant);
     const double minusT = b - determinant;
     const double plusT = b + determinant;
     if (minusT < kEpsilon && plusT < kEpsilon)
@@ -119,6 +120,68 @@ __device__ __forceinline__ void sweepTile(const double *__restrict__ tile, int t
                  firstIndex + i, best);
     testTriangle(mk(v0x.y, v0y.y, v0z.y), mk(e1x.y, e1y.y, e1z.y), mk(e2x.y, e2y.y, e2z.y), o, d,
                  firstIndex + i + 1, best);
+  }
+}
+
+// ---- two-stage sweep: division-free prefilter, exact test for the survivors -------------------
+// Stage 1 evaluates, for every triangle, the reference's own numerators X = tVec.pVec and
+// Y = dir.qVec and the determinant, and keeps the triangle unless it is PROVABLY rejected by
+// Scene.cpp:67,89.  With s = sign(det), Xs = s*X, Ys = s*Y, hi = |det|*(1 + 2^-40):
+//   u = rn(X * rn(1/det)) < 0   needs  Xs < 0   (rounding cannot change a sign; the -1e-300
+//                                                guard covers an underflow of the product to -0)
+//   u > 1                       needs  Xs > |det|*(1 + 2^-51) >= ...; so Xs <= hi keeps every
+//                                      triangle the exact test could accept; same for v, u+v.
+// Survivors (a handful per ray) are re-tested with the exact reference arithmetic
+// (testTriangle), in index order, so the nearest-hit decision is identical to the one-stage
+// sweep bit for bit while ~19 of ~48 FP64 instructions per triangle (the division and the
+// three scaled products) leave the hot loop.
+__device__ __forceinline__ bool prefilterTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 d) {
+  const V3 pVec = cross(d, e2);
+  const double det = dot(e1, pVec);
+  const V3 tVec = sub(o, v0);
+  const double x = dot(tVec, pVec);
+  const V3 qVec = cross(tVec, e1);
+  const double y = dot(d, qVec);
+  const double adet = fabs(det);
+  const double xs = det < 0 ? -x : x;
+  const double ys = det < 0 ? -y : y;
+  const double hi = adet * (1.0 + 0x1p-40);
+  return (adet >= kEpsilon) & (xs >= -1e-300) & (ys >= -1e-300) & (xs <= hi) & (xs + ys <= hi);
+}
+
+__device__ __forceinline__ void sweepTilePrefiltered(const double *__restrict__ tile, int tileTris,
+                                                     int count, int firstIndex, V3 o, V3 d,
+                                                     Nearest &best) {
+#pragma unroll 1
+  for (int chunk = 0; chunk < count; chunk += 64) {
+    const int chunkEnd = min(count, chunk + 64);
+    unsigned long long survivors = 0;
+#pragma unroll 1
+    for (int i = chunk; i < chunkEnd; i += 2) {
+      const double2 v0x = *reinterpret_cast<const double2 *>(tile + 0 * tileTris + i);
+      const double2 v0y = *reinterpret_cast<const double2 *>(tile + 1 * tileTris + i);
+      const double2 v0z = *reinterpret_cast<const double2 *>(tile + 2 * tileTris + i);
+      const double2 e1x = *reinterpret_cast<const double2 *>(tile + 3 * tileTris + i);
+      const double2 e1y = *reinterpret_cast<const double2 *>(tile + 4 * tileTris + i);
+      const double2 e1z = *reinterpret_cast<const double2 *>(tile + 5 * tileTris + i);
+      const double2 e2x = *reinterpret_cast<const double2 *>(tile + 6 * tileTris + i);
+      const double2 e2y = *reinterpret_cast<const double2 *>(tile + 7 * tileTris + i);
+      const double2 e2z = *reinterpret_cast<const double2 *>(tile + 8 * tileTris + i);
+      const bool a = prefilterTriangle(mk(v0x.x, v0y.x, v0z.x), mk(e1x.x, e1y.x, e1z.x),
+                                       mk(e2x.x, e2y.x, e2z.x), o, d);
+      const bool b = prefilterTriangle(mk(v0x.y, v0y.y, v0z.y), mk(e1x.y, e1y.y, e1z.y),
+                                       mk(e2x.y, e2y.y, e2z.y), o, d);
+      survivors |= (static_cast<unsigned long long>(a) | (static_cast<unsigned long long>(b) << 1))
+                   << (i - chunk);
+    }
+    while (survivors) { // ascending index: the serial loop's tie-break order
+      const int i = chunk + __ffsll(static_cast<long long>(survivors)) - 1;
+      survivors &= survivors - 1;
+      testTriangle(mk(tile[0 * tileTris + i], tile[1 * tileTris + i], tile[2 * tileTris + i]),
+                   mk(tile[3 * tileTris + i], tile[4 * tileTris + i], tile[5 * tileTris + i]),
+                   mk(tile[6 * tileTris + i], tile[7 * tileTris + i], tile[8 * tileTris + i]), o, d,
+                   firstIndex + i, best);
+    }
   }
 }
 
@@ -194,23 +257,6 @@ __device__ __forceinline__ void cameraRay(const DeviceCamera &cam, int pixelX, i
   origin = add(add(cam.centre, scale(scale(cam.axisX, cosA), radius)),
                scale(scale(cam.axisY, sinA), radius));
   direction = normalised(sub(focalPoint, origin));
-}
-
-// One stratified bounce (Scene.cpp:157-175): returns the new direction and whether the
-// specular branch was taken.  (uSample,vSample) of (numU,numV) strata; (ru,rv,rp) are the
-// three uniform draws in the reference's order.
-__device__ __forceinline__ bool sampleBounce(V3 normal, const Basis &basis, V3 incoming,
-                                             double reflectivity, double coneAngle, int uSample,
-                                             int numU, int vSample, int numV, double ru, double rv,
-                                             double rp, V3 &newDirection) {
-  const double u = (static_cast<double>(uSample) + ru) / static_cast<double>(numU);
-  const double v = (static_cast<double>(vSample) + rv) / static_cast<double>(numV);
-  if (rp < reflectivity) {
-    newDirection = coneSample(reflect(normal, incoming), coneAngle, u, v);
-    return true;
-  }
-  newDirection = hemisphereSample(basis, u, v);
-  return false;
 }
 
 // result += emission + radiance  /  result += emission + diffuse * radiance (Scene.cpp:168,172-174)

@@ -115,7 +115,23 @@ struct KeyedDraws {
 
 enum LaneMode : int { kNeedWork = 0, kTracing = 1, kFinished = 2 };
 
-template <int kBlock, int kMinBlocks>
+// Camera::randomRay for the keyed policy; once per ~45 casts, so out of line.
+static __device__ __noinline__ void keyedCameraRay(const DeviceCamera &camera, uint32_t key0, uint32_t pixel,
+                                            int px, int py, V3 &origin, V3 &direction) {
+  double ux, uy, ua, ur;
+  KeyedDraws{key0}.camera(pixel, ux, uy, ua, ur);
+  cameraRay(camera, px, py, ux, uy, ua, ur, origin, direction);
+}
+
+// A surface a bounce leaves from: what radiance() holds between its intersect() and its
+// sampling loop (Scene.cpp:135-152).
+struct Surface {
+  V3 position, normal, incoming, basisX, basisY;
+  double reflectivity;
+  uint32_t material;
+};
+
+template <int kBlock, int kMinBlocks, bool kPrefilter>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const KeyedArgs args) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   const DeviceScene &scene = args.scene;
@@ -139,14 +155,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const Ke
   uint64_t casts = 0;
   uint64_t sampleSlot = 0;       // where this sample's colour goes
   uint32_t pixel = 0;            // x + y*width (RNG key and framebuffer index)
-  KeyedDraws draws{0};
+  uint32_t key0 = 0;
   V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
-  int depth = 0;
-  // primary hit (depth 0) state, alive across the numSub sub-paths
-  V3 p0Position, p0Normal, p0Incoming, p0BasisX, p0BasisY;
-  double p0Reflectivity = 0;
-  uint32_t p0Material = 0;
-  bool p0Specular = false;
+  int depth = 0;                 // depth of the ray in flight
+  Surface primary{};             // the camera ray's hit, alive across its numSub sub-paths
+  bool primarySpecular = false;
   int subPath = 0;
   V3 acc = mk(0, 0, 0);
   // levels 1.. of the current sub-path: material index and branch taken
@@ -172,18 +185,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const Ke
           const int py = args.rowBegin + static_cast<int>(row) * args.rowStep;
           pixel = static_cast<uint32_t>(px) + static_cast<uint32_t>(py) * args.width;
           sampleSlot = item;
-          draws.key0 = static_cast<uint32_t>(args.seed + args.passBegin + static_cast<int>(passInBatch));
-          mode = kTracing;
+          key0 = static_cast<uint32_t>(args.seed + args.passBegin + static_cast<int>(passInBatch));
           depth = 0;
           if (args.maxDepth <= 0) { // radiance() returns Vec3() before intersecting (Scene.cpp:128-129)
             args.samples[3 * sampleSlot + 0] = 0.0;
             args.samples[3 * sampleSlot + 1] = 0.0;
             args.samples[3 * sampleSlot + 2] = 0.0;
-            mode = kNeedWork;
           } else {
-            double ux, uy, ua, ur;
-            draws.camera(pixel, ux, uy, ua, ur);
-            cameraRay(args.camera, px, py, ux, uy, ua, ur, origin, direction);
+            mode = kTracing;
+            keyedCameraRay(args.camera, key0, pixel, px, py, origin, direction);
           }
         } else {
           mode = kFinished;
@@ -199,122 +209,131 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const Ke
         break;
     }
 
-    // ---- 2. cast: spheres first, then every triangle (Scene.cpp:115-122) ----
+    // ---- 2. cast: spheres first, then every triangle (Scene.cpp:115-122); ONE sweep site ----
     Nearest best{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim};
     if (tracing) {
       ++casts;
       sweepSpheres(stream.smem.spheres, static_cast<int>(scene.numSpheres), origin, direction, best);
     }
-    if (resident) {
-      if (tracing && residentTile)
-        sweepTile(residentTile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris), 0,
-                  origin, direction, best);
-    } else {
-      for (uint32_t j = 0; j < scene.numTiles; ++j) {
-        const double *tile = stream.acquire();
-        if (tracing)
+    for (uint32_t j = 0; j < scene.numTiles; ++j) {
+      const double *tile = resident ? residentTile : stream.acquire();
+      if (tracing) {
+        if (kPrefilter)
+          sweepTilePrefiltered(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
+                               static_cast<int>(j * scene.tileTris), origin, direction, best);
+        else
           sweepTile(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
                     static_cast<int>(j * scene.tileTris), origin, direction, best);
-        stream.release();
       }
+      if (!resident)
+        stream.release();
     }
 
-    // ---- 3. shade / bounce / terminate ----
+    // ---- 3. what the cast means for this lane's path ----
     if (tracing) {
-      bool pathEnded = false; // the current sub-path (or the camera ray) has its radiance
+      bool ended = false;          // the ray in flight has its radiance (`incoming`)
+      bool bounce = false;         // launch a bounce from `surface` (or from `primary` at depth 0)
+      bool terminalPrimary = false;
       V3 incoming = mk(0, 0, 0);
-      const bool hitSomething = best.prim != kNoPrim;
-      if (!hitSomething) {
+      Surface surface{};
+      if (best.prim == kNoPrim) {
         incoming = environment; // Scene.cpp:132-133
-        pathEnded = true;
+        ended = true;
       } else {
         const HitInfo hit = finishHit(scene, stream.smem.spheres, origin, direction, best);
         const MaterialView mat = materialOf(scene, hit.material);
-        if (depth == 0) {
-          if (args.preview) { // Scene.cpp:137-138
-            incoming = mat.diffuse();
-            pathEnded = true;
-          } else {
-            p0Position = hit.position;
-            p0Normal = hit.normal;
-            p0Incoming = direction;
-            p0Material = hit.material;
-            p0Reflectivity = hitReflectivity(mat, hit, direction);
-            const Basis basis = basisFromZ(hit.normal);
-            p0BasisX = basis.x;
-            p0BasisY = basis.y;
-            acc = mk(0, 0, 0);
-            subPath = -1; // section 4 starts sub-path 0
-            incoming = mk(0, 0, 0);
-            pathEnded = true;
-          }
+        if (depth == 0 && args.preview) { // Scene.cpp:137-138
+          incoming = mat.diffuse();
+          ended = true;
         } else if (depth + 1 >= args.maxDepth) {
-          // The deepest level still evaluates its bounce loop, but every child returns
-          // Vec3() (Scene.cpp:128-129), so this level contributes its emission only.
+          // Deepest level: its bounce loop still runs, but every child returns Vec3()
+          // (Scene.cpp:128-129), so the level contributes its emission only.
           incoming = shadeTerm(mat, true, mk(0, 0, 0));
-          pathEnded = true;
+          ended = true;
+          terminalPrimary = depth == 0;
         } else {
-          const double reflectivity = hitReflectivity(mat, hit, direction);
+          surface.position = hit.position;
+          surface.normal = hit.normal;
+          surface.incoming = direction;
+          surface.material = hit.material;
+          surface.reflectivity = hitReflectivity(mat, hit, direction);
           const Basis basis = basisFromZ(hit.normal);
-          double ru, rv, rp;
-          draws.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
-          V3 newDirection;
-          const bool specular = sampleBounce(hit.normal, basis, direction, reflectivity,
-                                             mat.coneAngle(), 0, 1, 0, 1, ru, rv, rp, newDirection);
-          stackMaterial[depth] = static_cast<uint16_t>(hit.material);
-          stackSpecular[depth] = specular;
-          origin = hit.position;
-          direction = newDirection;
-          ++depth;
+          surface.basisX = basis.x;
+          surface.basisY = basis.y;
+          if (depth == 0) {
+            primary = surface;
+            acc = mk(0, 0, 0);
+            subPath = 0;
+          }
+          bounce = true;
         }
       }
 
-      // ---- 4. a finished (sub-)path: unwind, accumulate, start the next one ----
-      if (pathEnded) {
+      if (ended) {
         bool sampleDone = false;
-        V3 sampleColour = incoming;
-        if (depth == 0 && (!hitSomething || args.preview)) {
-          sampleDone = true; // camera ray missed, or preview
-        } else {
-          if (subPath >= 0) {
-            // incoming is the radiance returned to the deepest stacked level; unwind
-            // levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum, /1).
-            for (int level = depth - 1; level >= 1; --level)
-              incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
-            acc = add(acc, shadeTerm(materialOf(scene, p0Material), p0Specular, incoming));
+        V3 colour = incoming;
+        if (depth == 0) {
+          if (terminalPrimary) { // maxDepth == 1: numSub children, each Vec3()
+            acc = mk(0, 0, 0);
+            for (int k = 0; k < numSub; ++k)
+              acc = add(acc, incoming);
+            colour = scale(acc, invNumSub);
           }
+          sampleDone = true; // camera ray missed / preview / maxDepth == 1
+        } else {
+          // unwind levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum), then the
+          // primary hit's own term, in the reference's summation order
+          for (int level = depth - 1; level >= 1; --level)
+            incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
+          acc = add(acc, shadeTerm(materialOf(scene, primary.material), primarySpecular, incoming));
           ++subPath;
           if (subPath >= numSub) {
-            sampleColour = scale(acc, invNumSub); // Scene.cpp:178
-            sampleDone = true;
-          } else if (1 >= args.maxDepth) {
-            // maxDepth == 1: every child of the camera hit returns Vec3().
-            const MaterialView mat0 = materialOf(scene, p0Material);
-            for (; subPath < numSub; ++subPath)
-              acc = add(acc, shadeTerm(mat0, true, mk(0, 0, 0)));
-            sampleColour = scale(acc, invNumSub);
+            colour = scale(acc, invNumSub); // Scene.cpp:178
             sampleDone = true;
           } else {
-            const MaterialView mat0 = materialOf(scene, p0Material);
-            double ru, rv, rp;
-            draws.bounce(pixel, static_cast<uint32_t>(subPath), 0u, ru, rv, rp);
-            const Basis basis{p0BasisX, p0BasisY, p0Normal};
-            V3 newDirection;
-            p0Specular = sampleBounce(p0Normal, basis, p0Incoming, p0Reflectivity, mat0.coneAngle(),
-                                      subPath / args.firstBounceV, args.firstBounceU,
-                                      subPath % args.firstBounceV, args.firstBounceV, ru, rv, rp,
-                                      newDirection);
-            origin = p0Position;
-            direction = newDirection;
-            depth = 1;
+            depth = 0;
+            bounce = true; // next stratum of the camera hit
           }
         }
         if (sampleDone) {
-          args.samples[3 * sampleSlot + 0] = sampleColour.x;
-          args.samples[3 * sampleSlot + 1] = sampleColour.y;
-          args.samples[3 * sampleSlot + 2] = sampleColour.z;
+          args.samples[3 * sampleSlot + 0] = colour.x;
+          args.samples[3 * sampleSlot + 1] = colour.y;
+          args.samples[3 * sampleSlot + 2] = colour.z;
           mode = kNeedWork;
         }
+      }
+
+      // ---- 4. ONE bounce site (Scene.cpp:155-175) ----
+      if (bounce) {
+        const bool fromPrimary = depth == 0;
+        if (fromPrimary)
+          surface = primary;
+        double ru, rv, rp;
+        KeyedDraws{key0}.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
+        double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
+        if (fromPrimary) {
+          u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
+          v = ieeeDiv(static_cast<double>(subPath % args.firstBounceV) + rv, static_cast<double>(args.firstBounceV));
+        }
+        const MaterialView mat = materialOf(scene, surface.material);
+        bool specular;
+        V3 newDirection;
+        if (rp < surface.reflectivity) {
+          newDirection = coneSample(reflect(surface.normal, surface.incoming), mat.coneAngle(), u, v);
+          specular = true;
+        } else {
+          newDirection = hemisphereSample(Basis{surface.basisX, surface.basisY, surface.normal}, u, v);
+          specular = false;
+        }
+        if (fromPrimary) {
+          primarySpecular = specular;
+        } else {
+          stackMaterial[depth] = static_cast<uint16_t>(surface.material);
+          stackSpecular[depth] = specular;
+        }
+        origin = surface.position;
+        direction = newDirection;
+        ++depth;
       }
     }
     __syncwarp();
@@ -351,7 +370,7 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
   // The twist, 32 words at a time in index order; loads precede stores within a batch, so
   // word i sees old[i], old[i+1] and (i < 227 ? old : new)[i+397 mod 624] as the serial
   // algorithm does.
-  __device__ __forceinline__ void refill(unsigned lane) {
+  __device__ __noinline__ void refill(unsigned lane) {
     for (int batch = 0; batch < 640; batch += 32) {
       const int i = batch + static_cast<int>(lane);
       uint32_t value = 0;
@@ -380,6 +399,16 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
     const uint32_t lo = next(lane);
     const uint32_t hi = next(lane);
     return canonicalFromWords(lo, hi);
+  }
+  // Discards `count` outputs.
+  __device__ __forceinline__ void skip(uint32_t count, unsigned lane) {
+    while (count) {
+      if (index >= 624)
+        refill(lane);
+      const uint32_t step = min(count, static_cast<uint32_t>(624 - index));
+      index += static_cast<int>(step);
+      count -= step;
+    }
   }
 };
 
@@ -471,88 +500,131 @@ __global__ void __launch_bounds__(kWarps * 32) renderSequentialKernel(const Sequ
   uint16_t stackMaterial[kMaxDepth];
   bool stackSpecular[kMaxDepth];
 
-  for (int py = 0; py < args.height; ++py) {
-    for (int px = 0; px < args.width; ++px) {
-      V3 colour = mk(0, 0, 0);
-      // Camera::randomRay draws before radiance() checks the depth (Scene.cpp:214-215).
-      const double ux = rng.canonical(lane);
-      const double uy = rng.canonical(lane);
-      double ua = 0, ur = 0;
-      if (args.camera.apertureRadius != 0) {
-        ua = rng.canonical(lane);
-        ur = rng.canonical(lane);
-      }
-      V3 origin, direction;
-      cameraRay(args.camera, px, py, ux, uy, ua, ur, origin, direction);
-      if (args.maxDepth > 0) {
-        ++casts;
-        const Nearest first = warpIntersect(scene, origin, direction, lane, true, true, inf);
-        if (first.prim == kNoPrim) {
-          colour = environment;
+  // Everything below is warp-uniform: the 32 lanes only differ inside warpIntersect().
+  const int numPixels = args.width * args.height;
+  for (int pixelIndex = 0; pixelIndex < numPixels; ++pixelIndex) { // row-major (Scene.cpp:212-213)
+    const int px = pixelIndex % args.width;
+    const int py = pixelIndex / args.width;
+    // Camera::randomRay draws before radiance() looks at the depth (Scene.cpp:214-215).
+    const double ux = rng.canonical(lane);
+    const double uy = rng.canonical(lane);
+    double ua = 0, ur = 0;
+    if (args.camera.apertureRadius != 0) {
+      ua = rng.canonical(lane);
+      ur = rng.canonical(lane);
+    }
+    V3 origin, direction;
+    cameraRay(args.camera, px, py, ux, uy, ua, ur, origin, direction);
+
+    V3 colour = mk(0, 0, 0);
+    int depth = 0;
+    int subPath = 0;
+    Surface primary{};
+    bool primarySpecular = false;
+    V3 acc = mk(0, 0, 0);
+    bool sampleDone = args.maxDepth <= 0; // radiance() returns Vec3() at once (Scene.cpp:128-129)
+
+    while (!sampleDone) { // the keyed megakernel's state machine, one path at a time
+      ++casts;
+      const Nearest best = warpIntersect(scene, origin, direction, lane, true, true, inf);
+      bool ended = false, bounce = false, terminalPrimary = false;
+      V3 incoming = mk(0, 0, 0);
+      Surface surface{};
+      if (best.prim == kNoPrim) {
+        incoming = environment;
+        ended = true;
+      } else {
+        const HitInfo hit = finishHit(scene, scene.spheres, origin, direction, best);
+        const MaterialView mat = materialOf(scene, hit.material);
+        if (depth == 0 && args.preview) {
+          incoming = mat.diffuse();
+          ended = true;
+        } else if (depth + 1 >= args.maxDepth) {
+          // The deepest level draws its (u, v, p) triples and builds rays whose radiance is
+          // Vec3() (Scene.cpp:128-129,157-175): consume the stream, contribute the emission.
+          rng.skip(6u * static_cast<uint32_t>(depth == 0 ? numSub : 1), lane);
+          incoming = shadeTerm(mat, true, mk(0, 0, 0));
+          ended = true;
+          terminalPrimary = depth == 0;
         } else {
-          const HitInfo hit0 = finishHit(scene, scene.spheres, origin, direction, first);
-          const MaterialView mat0 = materialOf(scene, hit0.material);
-          if (args.preview) {
-            colour = mat0.diffuse();
-          } else {
-            const double reflectivity0 = hitReflectivity(mat0, hit0, direction);
-            const Basis basis0 = basisFromZ(hit0.normal);
-            const V3 incoming0 = direction;
-            V3 acc = mk(0, 0, 0);
-            for (int sub = 0; sub < numSub; ++sub) {
-              const double ru0 = rng.canonical(lane);
-              const double rv0 = rng.canonical(lane);
-              const double rp0 = rng.canonical(lane);
-              V3 dir;
-              const bool specular0 = sampleBounce(hit0.normal, basis0, incoming0, reflectivity0,
-                                                  mat0.coneAngle(), sub / args.firstBounceV,
-                                                  args.firstBounceU, sub % args.firstBounceV,
-                                                  args.firstBounceV, ru0, rv0, rp0, dir);
-              V3 org = hit0.position;
-              V3 incoming = mk(0, 0, 0);
-              int depth = 1;
-              // iterative form of the 1x1 recursion below the first bounce
-              for (;;) {
-                if (depth >= args.maxDepth) {
-                  incoming = mk(0, 0, 0);
-                  break;
-                }
-                ++casts;
-                const Nearest near = warpIntersect(scene, org, dir, lane, true, true, inf);
-                if (near.prim == kNoPrim) {
-                  incoming = environment;
-                  break;
-                }
-                const HitInfo hit = finishHit(scene, scene.spheres, org, dir, near);
-                const MaterialView mat = materialOf(scene, hit.material);
-                const double reflectivity = hitReflectivity(mat, hit, dir);
-                const Basis basis = basisFromZ(hit.normal);
-                const double ru = rng.canonical(lane);
-                const double rv = rng.canonical(lane);
-                const double rp = rng.canonical(lane);
-                V3 newDir;
-                const bool specular = sampleBounce(hit.normal, basis, dir, reflectivity, mat.coneAngle(),
-                                                   0, 1, 0, 1, ru, rv, rp, newDir);
-                stackMaterial[depth] = static_cast<uint16_t>(hit.material);
-                stackSpecular[depth] = specular;
-                org = hit.position;
-                dir = newDir;
-                ++depth;
-              }
-              for (int level = depth - 1; level >= 1; --level)
-                incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
-              acc = add(acc, shadeTerm(mat0, specular0, incoming));
-            }
+          surface.position = hit.position;
+          surface.normal = hit.normal;
+          surface.incoming = direction;
+          surface.material = hit.material;
+          surface.reflectivity = hitReflectivity(mat, hit, direction);
+          const Basis basis = basisFromZ(hit.normal);
+          surface.basisX = basis.x;
+          surface.basisY = basis.y;
+          if (depth == 0) {
+            primary = surface;
+            acc = mk(0, 0, 0);
+            subPath = 0;
+          }
+          bounce = true;
+        }
+      }
+      if (ended) {
+        colour = incoming;
+        if (depth == 0) {
+          if (terminalPrimary) {
+            acc = mk(0, 0, 0);
+            for (int k = 0; k < numSub; ++k)
+              acc = add(acc, incoming);
             colour = scale(acc, invNumSub);
+          }
+          sampleDone = true;
+        } else {
+          for (int level = depth - 1; level >= 1; --level)
+            incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
+          acc = add(acc, shadeTerm(materialOf(scene, primary.material), primarySpecular, incoming));
+          ++subPath;
+          if (subPath >= numSub) {
+            colour = scale(acc, invNumSub);
+            sampleDone = true;
+          } else {
+            depth = 0;
+            bounce = true;
           }
         }
       }
-      if (lane == 0) {
-        double *dst = passSamples + 3 * (static_cast<size_t>(px) + static_cast<size_t>(py) * args.width);
-        dst[0] = colour.x;
-        dst[1] = colour.y;
-        dst[2] = colour.z;
+      if (bounce) {
+        const bool fromPrimary = depth == 0;
+        if (fromPrimary)
+          surface = primary;
+        const double ru = rng.canonical(lane); // u, v, p in this order (Scene.cpp:157-161)
+        const double rv = rng.canonical(lane);
+        const double rp = rng.canonical(lane);
+        double u = ru, v = rv;
+        if (fromPrimary) {
+          u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
+          v = ieeeDiv(static_cast<double>(subPath % args.firstBounceV) + rv, static_cast<double>(args.firstBounceV));
+        }
+        const MaterialView mat = materialOf(scene, surface.material);
+        bool specular;
+        V3 newDirection;
+        if (rp < surface.reflectivity) {
+          newDirection = coneSample(reflect(surface.normal, surface.incoming), mat.coneAngle(), u, v);
+          specular = true;
+        } else {
+          newDirection = hemisphereSample(Basis{surface.basisX, surface.basisY, surface.normal}, u, v);
+          specular = false;
+        }
+        if (fromPrimary) {
+          primarySpecular = specular;
+        } else {
+          stackMaterial[depth] = static_cast<uint16_t>(surface.material);
+          stackSpecular[depth] = specular;
+        }
+        origin = surface.position;
+        direction = newDirection;
+        ++depth;
       }
+    }
+    if (lane == 0) {
+      double *dst = passSamples + 3 * static_cast<size_t>(pixelIndex);
+      dst[0] = colour.x;
+      dst[1] = colour.y;
+      dst[2] = colour.z;
     }
   }
   if (lane == 0)
@@ -626,12 +698,19 @@ __global__ void intersectKernel(const IntersectArgs args) {
     if (args.which != 1) {
       if (scene.numTiles == 1) {
         const double *tile = stream.acquire();
-        sweepTile(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris), 0, o, d, best);
+        if (args.prefilter)
+          sweepTilePrefiltered(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris), 0, o, d, best);
+        else
+          sweepTile(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris), 0, o, d, best);
       } else if (scene.numTiles > 1) {
         for (uint32_t j = 0; j < scene.numTiles; ++j) {
           const double *tile = stream.acquire();
-          sweepTile(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
-                    static_cast<int>(j * scene.tileTris), o, d, best);
+          if (args.prefilter)
+            sweepTilePrefiltered(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
+                                 static_cast<int>(j * scene.tileTris), o, d, best);
+          else
+            sweepTile(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
+                      static_cast<int>(j * scene.tileTris), o, d, best);
           stream.release();
         }
         stream.drain();
@@ -682,10 +761,10 @@ __global__ void fp64PeakKernel(double *sink, int iterations) {
 // =============================================================================================
 constexpr int kSequentialWarps = 2;
 
-template <int kBlock, int kMinBlocks>
+template <int kBlock, int kMinBlocks, bool kPrefilter>
 cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, size_t smemBytes, cudaStream_t stream,
                               int *blocksLaunched) {
-  auto kernel = renderKeyedKernel<kBlock, kMinBlocks>;
+  auto kernel = renderKeyedKernel<kBlock, kMinBlocks, kPrefilter>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smemBytes));
   if (err != cudaSuccess)
@@ -709,20 +788,19 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, size_t smemByte
 
 cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, size_t smemBytes, cudaStream_t stream,
                               int *blocksLaunched) {
-  // PTB200_KEYED_CONFIG selects a (threads per CTA, min CTAs per SM) pair, i.e. a register
-  // budget; used by tools/sweep_configs.py.  The default is what measured best on B200.
+  // PTB200_KEYED_CONFIG selects (threads per CTA, min CTAs per SM, sweep variant) for
+  // tools/sweep_configs.py.  The default is what measured best on B200.
   static const int config = [] {
     const char *env = getenv("PTB200_KEYED_CONFIG");
     return env ? atoi(env) : 0;
   }();
   switch (config) {
-  case 1: return launchKeyedConfig<384, 1>(args, numSms, smemBytes, stream, blocksLaunched); // 168 regs
-  case 2: return launchKeyedConfig<512, 1>(args, numSms, smemBytes, stream, blocksLaunched); // 128 regs
-  case 3: return launchKeyedConfig<256, 1>(args, numSms, smemBytes, stream, blocksLaunched); // 255 regs
-  case 4: return launchKeyedConfig<128, 3>(args, numSms, smemBytes, stream, blocksLaunched); // 168 regs
-  case 5: return launchKeyedConfig<128, 5>(args, numSms, smemBytes, stream, blocksLaunched); // 96 regs
-  case 6: return launchKeyedConfig<256, 3>(args, numSms, smemBytes, stream, blocksLaunched); // 80 regs
-  default: return launchKeyedConfig<256, 2>(args, numSms, smemBytes, stream, blocksLaunched); // 128 regs
+  case 1: return launchKeyedConfig<256, 2, false>(args, numSms, smemBytes, stream, blocksLaunched); // one-stage sweep
+  case 2: return launchKeyedConfig<512, 1, true>(args, numSms, smemBytes, stream, blocksLaunched);
+  case 3: return launchKeyedConfig<384, 1, true>(args, numSms, smemBytes, stream, blocksLaunched);  // 168 regs
+  case 4: return launchKeyedConfig<128, 4, true>(args, numSms, smemBytes, stream, blocksLaunched);
+  case 5: return launchKeyedConfig<256, 3, true>(args, numSms, smemBytes, stream, blocksLaunched);  // 80 regs
+  default: return launchKeyedConfig<256, 2, true>(args, numSms, smemBytes, stream, blocksLaunched); // 128 regs
   }
 }
 

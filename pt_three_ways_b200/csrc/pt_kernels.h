@@ -64,6 +64,7 @@ struct IntersectArgs {
   int32_t which;                   // 0 intersect, 1 spheres only, 2 triangles only
   double nearerThan;
   int32_t warpCooperative;
+  int32_t prefilter;               // two-stage sweep (sweepTilePrefiltered)
 };
 
 size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles);

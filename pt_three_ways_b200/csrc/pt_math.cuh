@@ -35,10 +35,17 @@ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
   return mk(fma(a.y, b.z, -(a.z * b.y)), fma(a.z, b.x, -(a.x * b.z)),
             fma(a.x, b.y, -(a.y * b.x)));
 }
+// Correctly rounded sqrt and division expand to ~50 SASS instructions each (MUFU seed, Newton
+// steps, exponent fix-ups).  Everywhere except the innermost triangle loop they are called
+// out of line: same IEEE results, but the megakernel's code stays inside the instruction cache.
+static __device__ __noinline__ double ieeeSqrt(double x) { return sqrt(x); }
+static __device__ __noinline__ double ieeeDiv(double a, double b) { return a / b; }
+static __device__ __noinline__ double ieeeRcpSqrt(double x) { return 1.0 / sqrt(x); }
+
 // Vec3::normalised (src/math/Vec3.impl.h:5-7): *this / length(), and operator/ multiplies by
 // the reciprocal (src/math/Vec3.h:51-54).
 __device__ __forceinline__ V3 normalised(V3 a) {
-  const double reciprocal = 1.0 / sqrt(dot(a, a));
+  const double reciprocal = ieeeRcpSqrt(dot(a, a));
   return scale(a, reciprocal);
 }
 // Ray::positionAlong (src/math/Ray.h:25-27).
@@ -91,7 +98,7 @@ __device__ __forceinline__ double asinCore(double z) {
   q = fma(q, z, 2.02094576023350569471e+00);
   q = fma(q, z, -2.40339491173441421878e+00);
   q = fma(q, z, 1.0);
-  return p / q;
+  return ieeeDiv(p, q);
 }
 __device__ __forceinline__ double arcCos(double x) { // x in [0, 1]
   if (x < 0.5) {
@@ -99,7 +106,7 @@ __device__ __forceinline__ double arcCos(double x) { // x in [0, 1]
     return 1.57079632679489655800e+00 - (x - fma(-x, r, 6.12323399573676603587e-17));
   }
   const double z = (1.0 - x) * 0.5;
-  const double s = sqrt(z);
+  const double s = ieeeSqrt(z);
   const double r = asinCore(z);
   return 2.0 * fma(s, r, s);
 }
@@ -144,15 +151,15 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 // rPerpendicular formula there, so (rPerp^2 + rPar^2)/2 == rPerp^2 exactly.
 __device__ __forceinline__ double reflectance(V3 normal, V3 incoming, double iorFrom,
                                               double iorTo) {
-  const double iorRatio = iorFrom / iorTo;
+  const double iorRatio = ieeeDiv(iorFrom, iorTo);
   const double cosThetaI = -dot(normal, incoming);
   const double sinThetaTSquared = (iorRatio * iorRatio) * fma(-cosThetaI, cosThetaI, 1.0);
   if (sinThetaTSquared > 1)
     return 1.0;
-  const double cosThetaT = sqrt(1 - sinThetaTSquared);
+  const double cosThetaT = ieeeSqrt(1 - sinThetaTSquared);
   const double a = iorFrom * cosThetaI;
   const double b = iorTo * cosThetaT;
-  const double rPerpendicular = (a - b) / (a + b);
+  const double rPerpendicular = ieeeDiv(a - b, a + b);
   return rPerpendicular * rPerpendicular;
 }
 // Norm3::reflect (src/math/Norm3.impl.h:41-44).
@@ -178,11 +185,12 @@ __device__ __forceinline__ V3 transform(const Basis &b, V3 p) {
             fma(b.z.y, p.z, fma(b.y.y, p.y, b.x.y * p.x)),
             fma(b.z.z, p.z, fma(b.y.z, p.y, b.x.z * p.x)));
 }
-// coneSample (src/math/Samples.cpp:6-19).
-__device__ __forceinline__ V3 coneSample(V3 direction, double coneTheta, double u, double v) {
+// coneSample (src/math/Samples.cpp:6-19).  Rare (specular picks only): kept out of line so the
+// hot loop's instruction footprint stays inside the instruction cache.
+static __device__ __noinline__ V3 coneSample(V3 direction, double coneTheta, double u, double v) {
   if (coneTheta < kEpsilon)
     return direction;
-  coneTheta = coneTheta * (1.0 - (2.0 * arcCos(u) / kPi));
+  coneTheta = coneTheta * (1.0 - ieeeDiv(2.0 * arcCos(u), kPi));
   double radius, zScale, sinT, cosT;
   sinCos(coneTheta, radius, zScale);
   const double randomTheta = v * 2 * kPi;
@@ -193,10 +201,10 @@ __device__ __forceinline__ V3 coneSample(V3 direction, double coneTheta, double 
 // hemisphereSample (src/math/Samples.cpp:21-30).
 __device__ __forceinline__ V3 hemisphereSample(const Basis &basis, double u, double v) {
   const double theta = (2 * kPi) * u;
-  const double radius = sqrt(v);
+  const double radius = ieeeSqrt(v);
   double sinT, cosT;
   sinCos(theta, sinT, cosT);
-  return normalised(transform(basis, mk(cosT * radius, sinT * radius, sqrt(1 - v))));
+  return normalised(transform(basis, mk(cosT * radius, sinT * radius, ieeeSqrt(1 - v))));
 }
 
 } // namespace ptb200

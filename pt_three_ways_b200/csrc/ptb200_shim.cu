@@ -641,7 +641,8 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
     return PTB200_OK;
   if (!rays || !out)
     return fail(PTB200_EINVAL, "null argument");
-  // bit 8 of `which` selects the warp-cooperative sweep of the sequential kernel (tests).
+  // Test hooks: bit 8 of `which` selects the warp-cooperative sweep of the sequential kernel,
+  // bit 9 the one-stage (no prefilter) per-lane sweep.
   const int32_t mode = which & 0xff;
   if (mode < 0 || mode > 2)
     return fail(PTB200_EINVAL, "which must be 0, 1 or 2");
@@ -668,6 +669,7 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
     a.which = mode;
     a.nearerThan = nearerThan;
     a.warpCooperative = (which & 0x100) ? 1 : 0;
+    a.prefilter = (which & 0x200) ? 0 : 1;
     const size_t smem = keyedSmemBytes(ctx->scene.numSpheres, ctx->scene.tileTris, ctx->scene.numTiles);
     PT_CUDA(launchIntersect(a, smem, ctx->stream));
     PT_CUDA(cudaMemcpyAsync(out, dOut.ptr, static_cast<size_t>(numRays) * sizeof(PtHit), cudaMemcpyDeviceToHost, ctx->stream));
