@@ -125,16 +125,19 @@ __device__ __forceinline__ void sweepTile(const double *__restrict__ tile, int t
 
 // ---- two-stage sweep: division-free prefilter, exact test for the survivors -------------------
 // Stage 1 evaluates, for every triangle, the reference's own numerators X = tVec.pVec and
-// Y = dir.qVec and the determinant, and keeps the triangle unless it is PROVABLY rejected by
-// Scene.cpp:67,89.  With s = sign(det), Xs = s*X, Ys = s*Y, hi = |det|*(1 + 2^-40):
-//   u = rn(X * rn(1/det)) < 0   needs  Xs < 0   (rounding cannot change a sign; the -1e-300
-//                                                guard covers an underflow of the product to -0)
-//   u > 1                       needs  Xs > |det|*(1 + 2^-51) >= ...; so Xs <= hi keeps every
-//                                      triangle the exact test could accept; same for v, u+v.
-// Survivors (a handful per ray) are re-tested with the exact reference arithmetic
-// (testTriangle), in index order, so the nearest-hit decision is identical to the one-stage
-// sweep bit for bit while ~19 of ~48 FP64 instructions per triangle (the division and the
-// three scaled products) leave the hot loop.
+// Y = dir.qVec and the determinant (24 FP64 instructions), and keeps the triangle unless it is
+// PROVABLY rejected by Scene.cpp:67,89.  With s = sign(det), Xs = s*X, Ys = s*Y:
+//   |det| < Epsilon         is only used when it is decided by the high 32 bits of |det|;
+//   u = rn(X*rn(1/det)) < 0 needs Xs < 0: rounding cannot change a sign, and the 1e-300 guard
+//                           (again on the high word) covers an underflow of the product to -0;
+//   v < 0                   likewise for Ys;
+//   u + v > 1               needs Xs + Ys > |det|*(1 + 2^-49) at least, so testing against
+//                           hi = |det|*(1 + 2^-40) can only keep MORE triangles; u > 1 is
+//                           implied by it once v >= 0.
+// Sign handling and the three "high word" tests are integer instructions (ALU pipe), leaving
+// 27 FP64 instructions per triangle.  Survivors (a handful per ray) are re-tested with the exact
+// reference arithmetic (testTriangle) in index order, so the nearest-hit decision is identical
+// to the one-stage sweep bit for bit; the division and the scaled products leave the hot loop.
 __device__ __forceinline__ bool prefilterTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 d) {
   const V3 pVec = cross(d, e2);
   const double det = dot(e1, pVec);
@@ -142,11 +145,19 @@ __device__ __forceinline__ bool prefilterTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 
   const double x = dot(tVec, pVec);
   const V3 qVec = cross(tVec, e1);
   const double y = dot(d, qVec);
-  const double adet = fabs(det);
-  const double xs = det < 0 ? -x : x;
-  const double ys = det < 0 ? -y : y;
+  const uint32_t detHi = static_cast<uint32_t>(__double2hiint(det));
+  const uint32_t sign = detHi & 0x80000000u;
+  const uint32_t xsHi = static_cast<uint32_t>(__double2hiint(x)) ^ sign;
+  const uint32_t ysHi = static_cast<uint32_t>(__double2hiint(y)) ^ sign;
+  const double xs = __hiloint2double(static_cast<int>(xsHi), __double2loint(x));
+  const double ys = __hiloint2double(static_cast<int>(ysHi), __double2loint(y));
+  const double adet = __hiloint2double(static_cast<int>(detHi & 0x7fffffffu), __double2loint(det));
   const double hi = adet * (1.0 + 0x1p-40);
-  return (adet >= kEpsilon) & (xs >= -1e-300) & (ys >= -1e-300) & (xs <= hi) & (xs + ys <= hi);
+  // high words: 1e-9 = 0x3E112E0B_E826D695, 1e-300 = 0x01A56E1F_C2F8F359
+  const bool detTooSmall = (detHi & 0x7fffffffu) < 0x3E112E0Bu;  // certainly |det| < Epsilon
+  const bool xNegative = xsHi > 0x81A56E1Fu;                      // certainly Xs < -1e-300
+  const bool yNegative = ysHi > 0x81A56E1Fu;
+  return !(detTooSmall | xNegative | yNegative) & (xs + ys <= hi);
 }
 
 __device__ __forceinline__ void sweepTilePrefiltered(const double *__restrict__ tile, int tileTris,

@@ -20,61 +20,64 @@ namespace ptb200 {
 // =============================================================================================
 // Shared-memory staging of the scene.
 // =============================================================================================
-struct SmemLayout {
-  uint64_t *bars;     // 2 mbarriers
-  double4 *spheres;   // numSpheres
-  double *tile[2];    // tile buffers (tile[1] only when numTiles > 1)
-};
-
-__device__ __forceinline__ SmemLayout carveSmem(unsigned char *base, const DeviceScene &scene) {
-  SmemLayout l;
-  l.bars = reinterpret_cast<uint64_t *>(base);
-  l.spheres = reinterpret_cast<double4 *>(base + 32);
-  const size_t sphereBytes = (static_cast<size_t>(scene.numSpheres) * sizeof(double4) + 127) & ~size_t(127);
-  l.tile[0] = reinterpret_cast<double *>(base + 128 + sphereBytes);
-  l.tile[1] = l.tile[0] + 9 * static_cast<size_t>(scene.tileTris);
-  return l;
+// Dynamic shared memory of a sweeping CTA (offsets from the 128-byte aligned base):
+//   [0, 16)            two mbarriers
+//   [32, 32 + 32 S)    spheres {centre, r^2}
+//   [tileOffset, ...)  tile buffer 0, then tile buffer 1 when the scene streams (numTiles > 1)
+// Pointers are always formed as  smemBase + offset  so the compiler keeps them in the shared
+// address space (LDS, not generic LD).
+__host__ __device__ inline uint32_t smemTileOffset(uint32_t numSpheres) {
+  return 128u + ((numSpheres * 32u + 127u) & ~127u);
 }
 
 __host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles) {
-  const size_t sphereBytes = (static_cast<size_t>(numSpheres) * 32 + 127) & ~size_t(127);
   const size_t tileBytes = static_cast<size_t>(tileTris) * 72;
-  return 128 + sphereBytes + tileBytes * (numTiles > 1 ? 2 : 1);
+  return smemTileOffset(numSpheres) + tileBytes * (numTiles > 1 ? 2 : 1);
 }
 
-// Streams tiles cyclically (0,1,..,n-1,0,1,..) through two buffers.  `consumed` counts tiles
-// this CTA has swept so far; buffer = consumed & 1, parity = (consumed >> 1) & 1.
+// Streams tiles cyclically (0,1,..,n-1,0,1,..) through two buffers with TMA bulk copies.
+// `consumed` counts tiles this CTA has swept so far; buffer = consumed & 1,
+// mbarrier parity = (consumed >> 1) & 1.
 struct TileStream {
-  const DeviceScene *scene;
-  SmemLayout smem;
+  unsigned char *smemBase;
+  const double *triSweep;
+  uint32_t tileTris, numTiles, tileOffset;
   uint32_t consumed;
-  uint32_t tileBytes;
 
-  __device__ __forceinline__ void issue(uint32_t sequence) { // one thread
-    const uint32_t buffer = sequence & 1;
-    const uint32_t tile = sequence % scene->numTiles;
-    mbarExpectTx(&smem.bars[buffer], tileBytes);
-    tmaLoad1D(smem.tile[buffer], scene->triSweep + static_cast<size_t>(tile) * 9 * scene->tileTris,
-              tileBytes, &smem.bars[buffer]);
+  __device__ __forceinline__ uint64_t *bar(uint32_t buffer) const {
+    return reinterpret_cast<uint64_t *>(smemBase) + buffer;
+  }
+  __device__ __forceinline__ double4 *spheres() const {
+    return reinterpret_cast<double4 *>(smemBase + 32);
+  }
+  __device__ __forceinline__ const double *tile(uint32_t buffer) const {
+    return reinterpret_cast<const double *>(smemBase + tileOffset + buffer * (tileTris * 72u));
+  }
+  __device__ __forceinline__ void issue(uint32_t sequence) const { // one thread
+    const uint32_t buffer = sequence & 1u;
+    const uint32_t tileIndex = sequence % numTiles;
+    const uint32_t bytes = tileTris * 72u;
+    mbarExpectTx(bar(buffer), bytes);
+    tmaLoad1D(const_cast<double *>(tile(buffer)), triSweep + static_cast<size_t>(tileIndex) * 9 * tileTris,
+              bytes, bar(buffer));
   }
   __device__ __forceinline__ void start() { // whole CTA, once
-    tileBytes = scene->tileTris * 72u;
     consumed = 0;
     if (threadIdx.x == 0) {
-      mbarInit(&smem.bars[0], 1);
-      mbarInit(&smem.bars[1], 1);
+      mbarInit(bar(0), 1);
+      mbarInit(bar(1), 1);
       fenceBarrierInit();
     }
     __syncthreads();
-    if (threadIdx.x == 0 && scene->numTiles > 0) {
+    if (threadIdx.x == 0 && numTiles > 0) {
       issue(0);
-      if (scene->numTiles > 1)
+      if (numTiles > 1)
         issue(1);
     }
   }
-  __device__ __forceinline__ const double *acquire() {
-    mbarWait(&smem.bars[consumed & 1], (consumed >> 1) & 1);
-    return smem.tile[consumed & 1];
+  __device__ __forceinline__ const double *acquire() const {
+    mbarWait(bar(consumed & 1u), (consumed >> 1) & 1u);
+    return tile(consumed & 1u);
   }
   __device__ __forceinline__ void release() { // whole CTA; only for numTiles > 1
     __syncthreads();
@@ -82,11 +85,16 @@ struct TileStream {
       issue(consumed + 2);
     ++consumed;
   }
-  __device__ __forceinline__ void drain() { // numTiles > 1: two copies are still in flight
-    mbarWait(&smem.bars[consumed & 1], (consumed >> 1) & 1);
-    mbarWait(&smem.bars[(consumed + 1) & 1], ((consumed + 1) >> 1) & 1);
+  __device__ __forceinline__ void drain() const { // numTiles > 1: two copies are still in flight
+    mbarWait(bar(consumed & 1u), (consumed >> 1) & 1u);
+    mbarWait(bar((consumed + 1) & 1u), ((consumed + 1) >> 1) & 1u);
   }
 };
+
+__device__ __forceinline__ TileStream makeTileStream(unsigned char *smemBase, const DeviceScene &scene) {
+  return TileStream{smemBase, scene.triSweep, scene.tileTris, scene.numTiles,
+                    smemTileOffset(scene.numSpheres), 0};
+}
 
 // =============================================================================================
 // Keyed (Philox) megakernel: one path per lane, persistent CTAs, work pulled from a ticket.
@@ -132,18 +140,18 @@ struct Surface {
 };
 
 template <int kBlock, int kMinBlocks, bool kPrefilter>
-__global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const KeyedArgs args) {
+__global__ void __launch_bounds__(kBlock, kMinBlocks)
+    renderKeyedKernel(const __grid_constant__ KeyedArgs args) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   const DeviceScene &scene = args.scene;
-  TileStream stream{&scene, carveSmem(smemRaw, scene), 0, 0};
+  TileStream stream = makeTileStream(smemRaw, scene);
   stream.start();
   for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += kBlock)
-    stream.smem.spheres[i] = scene.spheres[i];
+    stream.spheres()[i] = scene.spheres[i];
   __syncthreads();
   const bool resident = scene.numTiles <= 1;
-  const double *residentTile = nullptr;
   if (resident && scene.numTiles == 1)
-    residentTile = stream.acquire();
+    stream.acquire(); // the one tile stays in buffer 0 for the whole launch
 
   const unsigned lane = threadIdx.x & 31u;
   const int numSub = args.firstBounceU * args.firstBounceV;
@@ -169,6 +177,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const Ke
   for (;;) {
     // ---- 1. lanes without a path pull the next (pass, pixel) ticket, warp-aggregated ----
     const unsigned wantMask = __ballot_sync(kFullMask, mode == kNeedWork);
+    bool newSample = false;
     if (wantMask) {
       unsigned long long base = 0;
       const int leader = __ffs(wantMask) - 1;
@@ -193,12 +202,19 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const Ke
             args.samples[3 * sampleSlot + 2] = 0.0;
           } else {
             mode = kTracing;
-            keyedCameraRay(args.camera, key0, pixel, px, py, origin, direction);
+            newSample = true;
           }
         } else {
           mode = kFinished;
         }
       }
+    }
+    __syncwarp();
+    if (newSample) { // all lanes that start a sample this iteration generate their camera rays together
+      const uint32_t own = static_cast<uint32_t>(sampleSlot % args.ownPixels);
+      const int px = static_cast<int>(own % args.width);
+      const int py = args.rowBegin + static_cast<int>(own / args.width) * args.rowStep;
+      keyedCameraRay(args.camera, key0, pixel, px, py, origin, direction);
     }
     const bool tracing = mode == kTracing;
     if (resident) {
@@ -213,10 +229,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const Ke
     Nearest best{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim};
     if (tracing) {
       ++casts;
-      sweepSpheres(stream.smem.spheres, static_cast<int>(scene.numSpheres), origin, direction, best);
+      sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), origin, direction, best);
     }
     for (uint32_t j = 0; j < scene.numTiles; ++j) {
-      const double *tile = resident ? residentTile : stream.acquire();
+      const double *tile = resident ? stream.tile(0) : stream.acquire();
       if (tracing) {
         if (kPrefilter)
           sweepTilePrefiltered(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
@@ -230,111 +246,122 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) renderKeyedKernel(const Ke
     }
 
     // ---- 3. what the cast means for this lane's path ----
+    // The phases below are separated by __syncwarp() so that lanes arriving from different
+    // branches execute each (expensive) phase together instead of one convergence group at a
+    // time: profiling showed the bounce code running at ~8 of 32 lanes without them.
+    bool ended = false;          // the ray in flight has its radiance (`incoming`)
+    bool bounce = false;         // launch a bounce from `surface` (or from `primary` at depth 0)
+    bool terminalPrimary = false;
+    bool needSurface = false;
+    V3 incoming = mk(0, 0, 0);
+    HitInfo hit{};
     if (tracing) {
-      bool ended = false;          // the ray in flight has its radiance (`incoming`)
-      bool bounce = false;         // launch a bounce from `surface` (or from `primary` at depth 0)
-      bool terminalPrimary = false;
-      V3 incoming = mk(0, 0, 0);
-      Surface surface{};
       if (best.prim == kNoPrim) {
         incoming = environment; // Scene.cpp:132-133
         ended = true;
       } else {
-        const HitInfo hit = finishHit(scene, stream.smem.spheres, origin, direction, best);
-        const MaterialView mat = materialOf(scene, hit.material);
+        hit = finishHit(scene, stream.spheres(), origin, direction, best);
         if (depth == 0 && args.preview) { // Scene.cpp:137-138
-          incoming = mat.diffuse();
+          incoming = materialOf(scene, hit.material).diffuse();
           ended = true;
         } else if (depth + 1 >= args.maxDepth) {
           // Deepest level: its bounce loop still runs, but every child returns Vec3()
           // (Scene.cpp:128-129), so the level contributes its emission only.
-          incoming = shadeTerm(mat, true, mk(0, 0, 0));
+          incoming = shadeTerm(materialOf(scene, hit.material), true, mk(0, 0, 0));
           ended = true;
           terminalPrimary = depth == 0;
         } else {
-          surface.position = hit.position;
-          surface.normal = hit.normal;
-          surface.incoming = direction;
-          surface.material = hit.material;
-          surface.reflectivity = hitReflectivity(mat, hit, direction);
-          const Basis basis = basisFromZ(hit.normal);
-          surface.basisX = basis.x;
-          surface.basisY = basis.y;
-          if (depth == 0) {
-            primary = surface;
-            acc = mk(0, 0, 0);
-            subPath = 0;
-          }
-          bounce = true;
+          needSurface = true;
         }
       }
+    }
+    __syncwarp();
 
-      if (ended) {
-        bool sampleDone = false;
-        V3 colour = incoming;
-        if (depth == 0) {
-          if (terminalPrimary) { // maxDepth == 1: numSub children, each Vec3()
-            acc = mk(0, 0, 0);
-            for (int k = 0; k < numSub; ++k)
-              acc = add(acc, incoming);
-            colour = scale(acc, invNumSub);
-          }
-          sampleDone = true; // camera ray missed / preview / maxDepth == 1
-        } else {
-          // unwind levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum), then the
-          // primary hit's own term, in the reference's summation order
-          for (int level = depth - 1; level >= 1; --level)
-            incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
-          acc = add(acc, shadeTerm(materialOf(scene, primary.material), primarySpecular, incoming));
-          ++subPath;
-          if (subPath >= numSub) {
-            colour = scale(acc, invNumSub); // Scene.cpp:178
-            sampleDone = true;
-          } else {
-            depth = 0;
-            bounce = true; // next stratum of the camera hit
-          }
-        }
-        if (sampleDone) {
-          args.samples[3 * sampleSlot + 0] = colour.x;
-          args.samples[3 * sampleSlot + 1] = colour.y;
-          args.samples[3 * sampleSlot + 2] = colour.z;
-          mode = kNeedWork;
-        }
+    Surface surface{};
+    if (needSurface) { // Scene.cpp:135-152: reflectivity and the local basis at the hit
+      surface.position = hit.position;
+      surface.normal = hit.normal;
+      surface.incoming = direction;
+      surface.material = hit.material;
+      surface.reflectivity = hitReflectivity(materialOf(scene, hit.material), hit, direction);
+      const Basis basis = basisFromZ(hit.normal);
+      surface.basisX = basis.x;
+      surface.basisY = basis.y;
+      if (depth == 0) {
+        primary = surface;
+        acc = mk(0, 0, 0);
+        subPath = 0;
       }
+      bounce = true;
+    }
+    __syncwarp();
 
-      // ---- 4. ONE bounce site (Scene.cpp:155-175) ----
-      if (bounce) {
-        const bool fromPrimary = depth == 0;
-        if (fromPrimary)
-          surface = primary;
-        double ru, rv, rp;
-        KeyedDraws{key0}.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
-        double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
-        if (fromPrimary) {
-          u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
-          v = ieeeDiv(static_cast<double>(subPath % args.firstBounceV) + rv, static_cast<double>(args.firstBounceV));
+    if (ended) {
+      bool sampleDone = false;
+      V3 colour = incoming;
+      if (depth == 0) {
+        if (terminalPrimary) { // maxDepth == 1: numSub children, each Vec3()
+          acc = mk(0, 0, 0);
+          for (int k = 0; k < numSub; ++k)
+            acc = add(acc, incoming);
+          colour = scale(acc, invNumSub);
         }
-        const MaterialView mat = materialOf(scene, surface.material);
-        bool specular;
-        V3 newDirection;
-        if (rp < surface.reflectivity) {
-          newDirection = coneSample(reflect(surface.normal, surface.incoming), mat.coneAngle(), u, v);
-          specular = true;
+        sampleDone = true; // camera ray missed / preview / maxDepth == 1
+      } else {
+        // unwind levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum), then the
+        // primary hit's own term, in the reference's summation order
+        for (int level = depth - 1; level >= 1; --level)
+          incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
+        acc = add(acc, shadeTerm(materialOf(scene, primary.material), primarySpecular, incoming));
+        ++subPath;
+        if (subPath >= numSub) {
+          colour = scale(acc, invNumSub); // Scene.cpp:178
+          sampleDone = true;
         } else {
-          newDirection = hemisphereSample(Basis{surface.basisX, surface.basisY, surface.normal}, u, v);
-          specular = false;
+          depth = 0;
+          bounce = true; // next stratum of the camera hit
         }
-        if (fromPrimary) {
-          primarySpecular = specular;
-        } else {
-          stackMaterial[depth] = static_cast<uint16_t>(surface.material);
-          stackSpecular[depth] = specular;
-        }
-        origin = surface.position;
-        direction = newDirection;
-        ++depth;
       }
+      if (sampleDone) {
+        args.samples[3 * sampleSlot + 0] = colour.x;
+        args.samples[3 * sampleSlot + 1] = colour.y;
+        args.samples[3 * sampleSlot + 2] = colour.z;
+        mode = kNeedWork;
+      }
+    }
+    __syncwarp();
+
+    // ---- 4. ONE bounce site (Scene.cpp:155-175) ----
+    if (bounce) {
+      const bool fromPrimary = depth == 0;
+      if (fromPrimary)
+        surface = primary;
+      double ru, rv, rp;
+      KeyedDraws{key0}.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
+      double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
+      if (fromPrimary) {
+        u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
+        v = ieeeDiv(static_cast<double>(subPath % args.firstBounceV) + rv, static_cast<double>(args.firstBounceV));
+      }
+      bool specular;
+      V3 newDirection;
+      if (rp < surface.reflectivity) {
+        newDirection = coneSample(reflect(surface.normal, surface.incoming),
+                                  materialOf(scene, surface.material).coneAngle(), u, v);
+        specular = true;
+      } else {
+        newDirection = hemisphereSample(Basis{surface.basisX, surface.basisY, surface.normal}, u, v);
+        specular = false;
+      }
+      if (fromPrimary) {
+        primarySpecular = specular;
+      } else {
+        stackMaterial[depth] = static_cast<uint16_t>(surface.material);
+        stackSpecular[depth] = specular;
+      }
+      origin = surface.position;
+      direction = newDirection;
+      ++depth;
     }
     __syncwarp();
   }
@@ -480,7 +507,8 @@ __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o,
 }
 
 template <int kWarps>
-__global__ void __launch_bounds__(kWarps * 32) renderSequentialKernel(const SequentialArgs args) {
+__global__ void __launch_bounds__(kWarps * 32)
+    renderSequentialKernel(const __grid_constant__ SequentialArgs args) {
   __shared__ uint32_t mtState[kWarps][624];
   const DeviceScene &scene = args.scene;
   const unsigned lane = threadIdx.x & 31u;
@@ -634,7 +662,7 @@ __global__ void __launch_bounds__(kWarps * 32) renderSequentialKernel(const Sequ
 // =============================================================================================
 // Pass-ordered accumulation.
 // =============================================================================================
-__global__ void reducePassesKernel(const ReduceArgs args) {
+__global__ void reducePassesKernel(const __grid_constant__ ReduceArgs args) {
   const uint32_t own = blockIdx.x * blockDim.x + threadIdx.x;
   if (own >= args.ownPixels)
     return;
@@ -660,13 +688,13 @@ __global__ void reducePassesKernel(const ReduceArgs args) {
 // Scene::intersect for tests: one ray per lane (block-wide sweep from shared memory, the
 // megakernel's path) or one ray per warp (the sequential kernel's path).
 // =============================================================================================
-__global__ void intersectKernel(const IntersectArgs args) {
+__global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   const DeviceScene &scene = args.scene;
-  TileStream stream{&scene, carveSmem(smemRaw, scene), 0, 0};
+  TileStream stream = makeTileStream(smemRaw, scene);
   stream.start();
   for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += blockDim.x)
-    stream.smem.spheres[i] = scene.spheres[i];
+    stream.spheres()[i] = scene.spheres[i];
   __syncthreads();
   const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = ray < args.numRays;
@@ -694,7 +722,7 @@ __global__ void intersectKernel(const IntersectArgs args) {
       stream.acquire();
   } else {
     if (args.which != 2)
-      sweepSpheres(stream.smem.spheres, static_cast<int>(scene.numSpheres), o, d, best);
+      sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), o, d, best);
     if (args.which != 1) {
       if (scene.numTiles == 1) {
         const double *tile = stream.acquire();
@@ -725,7 +753,7 @@ __global__ void intersectKernel(const IntersectArgs args) {
     return;
   PtHitDevice out{};
   if (best.prim != kNoPrim) {
-    const HitInfo hit = finishHit(scene, stream.smem.spheres, o, d, best);
+    const HitInfo hit = finishHit(scene, stream.spheres(), o, d, best);
     out.hit = 1;
     out.inside = hit.inside ? 1 : 0;
     out.material = static_cast<int32_t>(hit.material);
