@@ -23,9 +23,10 @@ struct DeviceScene {
   const double4 *spheres;     // [numSpheres] {centre xyz, radius^2}   (Sphere.h:7-12)
   const uint32_t *sphereMaterial;
   const double *materials;    // [numMaterials][9] MaterialSpec order
+  const float *triFilter;     // [numTiles][13][tileTris] fp32 stage-0 data (see buildFilterKernel)
   uint32_t numTriangles;
   uint32_t numSpheres;
-  uint32_t tileTris;          // triangles per tile (even)
+  uint32_t tileTris;          // triangles per tile (multiple of 4)
   uint32_t numTiles;
   double environment[3];
 };
@@ -192,6 +193,78 @@ __device__ __forceinline__ void sweepTilePrefiltered(const double *__restrict__ 
                    mk(tile[3 * tileTris + i], tile[4 * tileTris + i], tile[5 * tileTris + i]),
                    mk(tile[6 * tileTris + i], tile[7 * tileTris + i], tile[8 * tileTris + i]), o, d,
                    firstIndex + i, best);
+    }
+  }
+}
+
+// ---- three-stage sweep: conservative FP32 stage 0, exact FP64 test for the survivors ----------
+// Stage 0 evaluates Moller-Trumbore's det, X = tVec.pVec, Y = dir.qVec in FP32 from FP32 copies
+// of the triangle and of the ray, and rejects a triangle only when the reference's FP64 test
+// CERTAINLY rejects it, using per-triangle absolute error bounds built by buildFilterKernel:
+//   Ed >= |det32 - det|,  Ex >= |X32 - X|,  Ey >= |Y32 - Y|    (2^-18 x the magnitudes involved:
+//   64 FP32 roundoffs, about 4x what a forward error analysis of the 24 operations needs).
+// With s = sign(det32), certain rejection needs |det32| > Ed (the sign is then the reference's)
+// and one of   s*X32 < -2Ex   (=> u < 0),   s*Y32 < -2Ey   (=> v < 0),
+//              s*(X32+Y32) > |det32|*(1+2^-20) + Ed + Ex + Ey   (=> u + v > 1).
+// NaNs keep the triangle.  Survivors are re-tested with the exact reference arithmetic
+// (testTriangle on the FP64 data in global memory/L1) in index order, so results are bit-identical
+// to the one-stage sweep; the FP64 pipe only sees a handful of triangles per ray.
+struct Stage0Ray {
+  float ox, oy, oz, dx, dy, dz;
+};
+__device__ __forceinline__ bool stage0Keep(float v0x, float v0y, float v0z, float e1x, float e1y,
+                                           float e1z, float e2x, float e2y, float e2z, float ed,
+                                           float kx, float ky, float k3, const Stage0Ray &r) {
+  const float px = fmaf(r.dy, e2z, -(r.dz * e2y));
+  const float py = fmaf(r.dz, e2x, -(r.dx * e2z));
+  const float pz = fmaf(r.dx, e2y, -(r.dy * e2x));
+  const float det = fmaf(e1z, pz, fmaf(e1y, py, e1x * px));
+  const float tx = r.ox - v0x, ty = r.oy - v0y, tz = r.oz - v0z;
+  const float x = fmaf(tz, pz, fmaf(ty, py, tx * px));
+  const float qx = fmaf(ty, e1z, -(tz * e1y));
+  const float qy = fmaf(tz, e1x, -(tx * e1z));
+  const float qz = fmaf(tx, e1y, -(ty * e1x));
+  const float y = fmaf(r.dz, qz, fmaf(r.dy, qy, r.dx * qx));
+  const uint32_t sign = __float_as_uint(det) & 0x80000000u;
+  const float xs = __uint_as_float(__float_as_uint(x) ^ sign);
+  const float ys = __uint_as_float(__float_as_uint(y) ^ sign);
+  const float adet = fabsf(det);
+  const bool certain = (xs < -kx) | (ys < -ky) | (xs + ys > fmaf(adet, 1.0f + 0x1p-20f, k3));
+  return (adet <= ed) | !certain;
+}
+
+// `filter` is the FP32 tile in shared memory ([13][tileTris]); `exact` the same tile's FP64
+// sweep data in global memory ([9][tileTris]).  count is a multiple of 4.
+__device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter,
+                                                const double *__restrict__ exact, int tileTris,
+                                                int count, int firstIndex, V3 o, V3 d,
+                                                Nearest &best) {
+  const Stage0Ray r{static_cast<float>(o.x), static_cast<float>(o.y), static_cast<float>(o.z),
+                    static_cast<float>(d.x), static_cast<float>(d.y), static_cast<float>(d.z)};
+#pragma unroll 1
+  for (int chunk = 0; chunk < count; chunk += 64) {
+    const int chunkEnd = min(count, chunk + 64);
+    unsigned long long survivors = 0;
+#pragma unroll 1
+    for (int i = chunk; i < chunkEnd; i += 4) {
+      float4 a[13];
+#pragma unroll
+      for (int k = 0; k < 13; ++k)
+        a[k] = *reinterpret_cast<const float4 *>(filter + k * tileTris + i);
+      const unsigned keep =
+          (stage0Keep(a[0].x, a[1].x, a[2].x, a[3].x, a[4].x, a[5].x, a[6].x, a[7].x, a[8].x, a[9].x, a[10].x, a[11].x, a[12].x, r) ? 1u : 0u) |
+          (stage0Keep(a[0].y, a[1].y, a[2].y, a[3].y, a[4].y, a[5].y, a[6].y, a[7].y, a[8].y, a[9].y, a[10].y, a[11].y, a[12].y, r) ? 2u : 0u) |
+          (stage0Keep(a[0].z, a[1].z, a[2].z, a[3].z, a[4].z, a[5].z, a[6].z, a[7].z, a[8].z, a[9].z, a[10].z, a[11].z, a[12].z, r) ? 4u : 0u) |
+          (stage0Keep(a[0].w, a[1].w, a[2].w, a[3].w, a[4].w, a[5].w, a[6].w, a[7].w, a[8].w, a[9].w, a[10].w, a[11].w, a[12].w, r) ? 8u : 0u);
+      survivors |= static_cast<unsigned long long>(keep) << (i - chunk);
+    }
+    while (survivors) { // ascending index: the serial loop's tie-break order
+      const int i = chunk + __ffsll(static_cast<long long>(survivors)) - 1;
+      survivors &= survivors - 1;
+      testTriangle(mk(__ldg(exact + 0 * tileTris + i), __ldg(exact + 1 * tileTris + i), __ldg(exact + 2 * tileTris + i)),
+                   mk(__ldg(exact + 3 * tileTris + i), __ldg(exact + 4 * tileTris + i), __ldg(exact + 5 * tileTris + i)),
+                   mk(__ldg(exact + 6 * tileTris + i), __ldg(exact + 7 * tileTris + i), __ldg(exact + 8 * tileTris + i)),
+                   o, d, firstIndex + i, best);
     }
   }
 }
