@@ -19,10 +19,12 @@ constexpr uint32_t kFullMask = 0xffffffffu;
 // Tiles are padded with all-zero triangles (det == 0 -> skipped, Scene.cpp:66-68).
 struct DeviceScene {
   const double *triSweep;     // [numTiles][9][tileTris]
-  const double4 *triShade;    // [numTriangles] {shading normal xyz, material index (as double)}
+  const double4 *triShade;    // [numTriangles][4] {normal xyz, material} {frontX xyz, frontY.x}
+                              //   {frontY yz, backX xy} {backX z, backY xyz}: the shading normal and the
+                              //   OrthoNormalBasis::fromZ of +normal / -normal, precomputed at upload
   const double4 *spheres;     // [numSpheres] {centre xyz, radius^2}   (Sphere.h:7-12)
   const uint32_t *sphereMaterial;
-  const double *materials;    // [numMaterials][9] MaterialSpec order
+  const double *materials;    // [numMaterials][10] MaterialSpec order + 1/indexOfRefraction
   const float *triFilter;     // [numTiles][13][tileTris] fp32 stage-0 data (see buildFilterKernel)
   uint32_t numTriangles;
   uint32_t numSpheres;
@@ -47,6 +49,7 @@ constexpr int kNoPrim = 0x7fffffff;
 struct HitInfo {
   V3 position, normal;
   uint32_t material;
+  int triangle;        // >= 0: the hit triangle (its precomputed basis can be loaded), else -1
   bool inside;
 };
 
@@ -282,16 +285,42 @@ __device__ __forceinline__ HitInfo finishHit(const DeviceScene &scene,
     hit.inside = dot(normal, d) > 0;
     hit.normal = hit.inside ? neg(normal) : normal;
     hit.material = __ldg(scene.sphereMaterial + i);
+    hit.triangle = -1;
   } else {
-    // Three equal vertex normals make Scene.cpp:99-107 independent of u,v; the value is
-    // precomputed at upload (ptb200_shim.cu: shadingNormal()).
-    const double4 sh = ldgDouble4(scene.triShade + best.prim);
+    // Three equal vertex normals make Scene.cpp:99-107 independent of u,v; the value and the
+    // local bases of both orientations are precomputed at upload (ptb200_shim.cu) with the
+    // same arithmetic basisFromZ() uses, so loading them is bit-identical to recomputing.
+    const double4 r0 = ldgDouble4(scene.triShade + 4 * static_cast<size_t>(best.prim));
     const bool backfacing = best.det < kEpsilon;
     hit.inside = backfacing;
-    hit.normal = backfacing ? mk(-sh.x, -sh.y, -sh.z) : mk(sh.x, sh.y, sh.z);
-    hit.material = static_cast<uint32_t>(sh.w);
+    hit.material = static_cast<uint32_t>(r0.w);
+    hit.triangle = best.prim;
+    hit.normal = backfacing ? mk(-r0.x, -r0.y, -r0.z) : mk(r0.x, r0.y, r0.z);
   }
   return hit;
+}
+
+// OrthoNormalBasis::fromZ(hit.normal): loaded for triangles (precomputed for both orientations
+// at upload with basisFromZ()'s arithmetic), computed for spheres.
+__device__ __forceinline__ void hitBasis(const DeviceScene &scene, const HitInfo &hit, V3 &basisX,
+                                         V3 &basisY) {
+  if (hit.triangle >= 0) {
+    const double4 *record = scene.triShade + 4 * static_cast<size_t>(hit.triangle);
+    const double4 r2 = ldgDouble4(record + 2);
+    if (hit.inside) { // backfacing
+      const double4 r3 = ldgDouble4(record + 3);
+      basisX = mk(r2.z, r2.w, r3.x);
+      basisY = mk(r3.y, r3.z, r3.w);
+    } else {
+      const double4 r1 = ldgDouble4(record + 1);
+      basisX = mk(r1.x, r1.y, r1.z);
+      basisY = mk(r1.w, r2.x, r2.y);
+    }
+  } else {
+    const Basis basis = basisFromZ(hit.normal);
+    basisX = basis.x;
+    basisY = basis.y;
+  }
 }
 
 struct MaterialView {
@@ -301,9 +330,10 @@ struct MaterialView {
   __device__ __forceinline__ double indexOfRefraction() const { return __ldg(m + 6); }
   __device__ __forceinline__ double reflectivity() const { return __ldg(m + 7); }
   __device__ __forceinline__ double coneAngle() const { return __ldg(m + 8); }
+  __device__ __forceinline__ double inverseIndexOfRefraction() const { return __ldg(m + 9); }
 };
 __device__ __forceinline__ MaterialView materialOf(const DeviceScene &scene, uint32_t index) {
-  return MaterialView{scene.materials + 9 * static_cast<size_t>(index)};
+  return MaterialView{scene.materials + 10 * static_cast<size_t>(index)};
 }
 
 // Reflectivity at a hit (Scene.cpp:140-146).
@@ -312,8 +342,11 @@ __device__ __forceinline__ double hitReflectivity(const MaterialView &mat, const
   const double fixed = mat.reflectivity();
   if (!(fixed < 0))
     return fixed;
+  // iorFrom / iorTo is ior / 1.0 == ior from inside, 1.0 / ior (precomputed, same IEEE
+  // division) from outside.
   const double ior = mat.indexOfRefraction();
-  return reflectance(hit.normal, incoming, hit.inside ? ior : 1.0, hit.inside ? 1.0 : ior);
+  return reflectance(hit.normal, incoming, hit.inside ? ior : 1.0, hit.inside ? 1.0 : ior,
+                     hit.inside ? ior : mat.inverseIndexOfRefraction());
 }
 
 // Camera::randomRay + rayFromUnit (Camera.h:20-37,54-60) given its four uniform draws.

@@ -30,8 +30,14 @@ __host__ __device__ inline uint32_t smemTileOffset(uint32_t numSpheres) {
   return 128u + ((numSpheres * 32u + 127u) & ~127u);
 }
 
-__host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles) {
-  const size_t tileBytes = static_cast<size_t>(tileTris) * 72;
+constexpr uint32_t kExactBytesPerTriangle = 72;  // 9 doubles
+constexpr uint32_t kFilterBytesPerTriangle = 52; // 13 floats
+__host__ __device__ inline uint32_t sweepBytesPerTriangle(int sweep) {
+  return sweep == 2 ? kFilterBytesPerTriangle : kExactBytesPerTriangle;
+}
+
+__host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep) {
+  const size_t tileBytes = static_cast<size_t>(tileTris) * sweepBytesPerTriangle(sweep);
   return smemTileOffset(numSpheres) + tileBytes * (numTiles > 1 ? 2 : 1);
 }
 
@@ -40,8 +46,8 @@ __host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t 
 // mbarrier parity = (consumed >> 1) & 1.
 struct TileStream {
   unsigned char *smemBase;
-  const double *triSweep;
-  uint32_t tileTris, numTiles, tileOffset;
+  const unsigned char *source; // tile-major array in HBM: triSweep (FP64) or triFilter (FP32)
+  uint32_t tileBytes, numTiles, tileOffset;
   uint32_t consumed;
 
   __device__ __forceinline__ uint64_t *bar(uint32_t buffer) const {
@@ -50,16 +56,15 @@ struct TileStream {
   __device__ __forceinline__ double4 *spheres() const {
     return reinterpret_cast<double4 *>(smemBase + 32);
   }
-  __device__ __forceinline__ const double *tile(uint32_t buffer) const {
-    return reinterpret_cast<const double *>(smemBase + tileOffset + buffer * (tileTris * 72u));
+  __device__ __forceinline__ const unsigned char *tile(uint32_t buffer) const {
+    return smemBase + tileOffset + buffer * tileBytes;
   }
   __device__ __forceinline__ void issue(uint32_t sequence) const { // one thread
     const uint32_t buffer = sequence & 1u;
     const uint32_t tileIndex = sequence % numTiles;
-    const uint32_t bytes = tileTris * 72u;
-    mbarExpectTx(bar(buffer), bytes);
-    tmaLoad1D(const_cast<double *>(tile(buffer)), triSweep + static_cast<size_t>(tileIndex) * 9 * tileTris,
-              bytes, bar(buffer));
+    mbarExpectTx(bar(buffer), tileBytes);
+    tmaLoad1D(const_cast<unsigned char *>(tile(buffer)), source + static_cast<size_t>(tileIndex) * tileBytes,
+              tileBytes, bar(buffer));
   }
   __device__ __forceinline__ void start() { // whole CTA, once
     consumed = 0;
@@ -75,7 +80,7 @@ struct TileStream {
         issue(1);
     }
   }
-  __device__ __forceinline__ const double *acquire() const {
+  __device__ __forceinline__ const unsigned char *acquire() const {
     mbarWait(bar(consumed & 1u), (consumed >> 1) & 1u);
     return tile(consumed & 1u);
   }
@@ -91,9 +96,29 @@ struct TileStream {
   }
 };
 
-__device__ __forceinline__ TileStream makeTileStream(unsigned char *smemBase, const DeviceScene &scene) {
-  return TileStream{smemBase, scene.triSweep, scene.tileTris, scene.numTiles,
+__device__ __forceinline__ TileStream makeTileStream(unsigned char *smemBase, const DeviceScene &scene,
+                                                     int sweep) {
+  return TileStream{smemBase,
+                    sweep == 2 ? reinterpret_cast<const unsigned char *>(scene.triFilter)
+                               : reinterpret_cast<const unsigned char *>(scene.triSweep),
+                    scene.tileTris * sweepBytesPerTriangle(sweep), scene.numTiles,
                     smemTileOffset(scene.numSpheres), 0};
+}
+
+// One tile of the sweep, whichever variant: `tile` is what the TileStream staged.
+template <int kSweep>
+__device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const unsigned char *tile,
+                                                uint32_t tileIndex, V3 o, V3 d, Nearest &best) {
+  const int tileTris = static_cast<int>(scene.tileTris);
+  const int first = static_cast<int>(tileIndex * scene.tileTris);
+  if (kSweep == 2)
+    sweepTileStage0(reinterpret_cast<const float *>(tile),
+                    scene.triSweep + static_cast<size_t>(tileIndex) * 9 * scene.tileTris, tileTris, tileTris,
+                    first, o, d, best);
+  else if (kSweep == 1)
+    sweepTilePrefiltered(reinterpret_cast<const double *>(tile), tileTris, tileTris, first, o, d, best);
+  else
+    sweepTile(reinterpret_cast<const double *>(tile), tileTris, tileTris, first, o, d, best);
 }
 
 // =============================================================================================
@@ -139,12 +164,12 @@ struct Surface {
   uint32_t material;
 };
 
-template <int kBlock, int kMinBlocks, bool kPrefilter>
+template <int kBlock, int kMinBlocks, int kSweep>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
     renderKeyedKernel(const __grid_constant__ KeyedArgs args) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   const DeviceScene &scene = args.scene;
-  TileStream stream = makeTileStream(smemRaw, scene);
+  TileStream stream = makeTileStream(smemRaw, scene, kSweep);
   stream.start();
   for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += kBlock)
     stream.spheres()[i] = scene.spheres[i];
@@ -232,15 +257,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), origin, direction, best);
     }
     for (uint32_t j = 0; j < scene.numTiles; ++j) {
-      const double *tile = resident ? stream.tile(0) : stream.acquire();
-      if (tracing) {
-        if (kPrefilter)
-          sweepTilePrefiltered(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
-                               static_cast<int>(j * scene.tileTris), origin, direction, best);
-        else
-          sweepTile(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
-                    static_cast<int>(j * scene.tileTris), origin, direction, best);
-      }
+      const unsigned char *tile = resident ? stream.tile(0) : stream.acquire();
+      if (tracing)
+        sweepStagedTile<kSweep>(scene, tile, j, origin, direction, best);
       if (!resident)
         stream.release();
     }
@@ -284,9 +303,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       surface.incoming = direction;
       surface.material = hit.material;
       surface.reflectivity = hitReflectivity(materialOf(scene, hit.material), hit, direction);
-      const Basis basis = basisFromZ(hit.normal);
-      surface.basisX = basis.x;
-      surface.basisY = basis.y;
+      hitBasis(scene, hit, surface.basisX, surface.basisY);
       if (depth == 0) {
         primary = surface;
         acc = mk(0, 0, 0);
@@ -340,8 +357,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       KeyedDraws{key0}.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
       double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
       if (fromPrimary) {
-        u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
-        v = ieeeDiv(static_cast<double>(subPath % args.firstBounceV) + rv, static_cast<double>(args.firstBounceV));
+        // x / n == x * (1/n) exactly when n is a power of two (the default 4x4 strata)
+        const double su = static_cast<double>(subPath / args.firstBounceV) + ru;
+        const double sv = static_cast<double>(subPath % args.firstBounceV) + rv;
+        u = args.firstBounceUPow2 ? su * args.invFirstBounceU : ieeeDiv(su, static_cast<double>(args.firstBounceU));
+        v = args.firstBounceVPow2 ? sv * args.invFirstBounceV : ieeeDiv(sv, static_cast<double>(args.firstBounceV));
       }
       bool specular;
       V3 newDirection;
@@ -580,9 +600,7 @@ __global__ void __launch_bounds__(kWarps * 32)
           surface.incoming = direction;
           surface.material = hit.material;
           surface.reflectivity = hitReflectivity(mat, hit, direction);
-          const Basis basis = basisFromZ(hit.normal);
-          surface.basisX = basis.x;
-          surface.basisY = basis.y;
+          hitBasis(scene, hit, surface.basisX, surface.basisY);
           if (depth == 0) {
             primary = surface;
             acc = mk(0, 0, 0);
@@ -691,7 +709,7 @@ __global__ void reducePassesKernel(const __grid_constant__ ReduceArgs args) {
 __global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
   const DeviceScene &scene = args.scene;
-  TileStream stream = makeTileStream(smemRaw, scene);
+  TileStream stream = makeTileStream(smemRaw, scene, args.sweep);
   stream.start();
   for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += blockDim.x)
     stream.spheres()[i] = scene.spheres[i];
@@ -724,25 +742,19 @@ __global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
     if (args.which != 2)
       sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), o, d, best);
     if (args.which != 1) {
-      if (scene.numTiles == 1) {
-        const double *tile = stream.acquire();
-        if (args.prefilter)
-          sweepTilePrefiltered(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris), 0, o, d, best);
+      for (uint32_t j = 0; j < scene.numTiles; ++j) {
+        const unsigned char *tile = stream.acquire();
+        if (args.sweep == 2)
+          sweepStagedTile<2>(scene, tile, j, o, d, best);
+        else if (args.sweep == 1)
+          sweepStagedTile<1>(scene, tile, j, o, d, best);
         else
-          sweepTile(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris), 0, o, d, best);
-      } else if (scene.numTiles > 1) {
-        for (uint32_t j = 0; j < scene.numTiles; ++j) {
-          const double *tile = stream.acquire();
-          if (args.prefilter)
-            sweepTilePrefiltered(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
-                                 static_cast<int>(j * scene.tileTris), o, d, best);
-          else
-            sweepTile(tile, static_cast<int>(scene.tileTris), static_cast<int>(scene.tileTris),
-                      static_cast<int>(j * scene.tileTris), o, d, best);
+          sweepStagedTile<0>(scene, tile, j, o, d, best);
+        if (scene.numTiles > 1)
           stream.release();
-        }
-        stream.drain();
       }
+      if (scene.numTiles > 1)
+        stream.drain();
     } else if (scene.numTiles > 1) {
       stream.drain();
     } else if (scene.numTiles == 1) {
@@ -763,6 +775,86 @@ __global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
     out.normal[0] = hit.normal.x; out.normal[1] = hit.normal.y; out.normal[2] = hit.normal.z;
   }
   args.out[ray] = out;
+}
+
+// =============================================================================================
+// FP32 stage-0 data: float copies of {v0, e1, e2} and the per-triangle error bounds.
+// =============================================================================================
+__global__ void buildFilterKernel(const __grid_constant__ BuildFilterArgs args) {
+  const DeviceScene &scene = args.scene;
+  const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= scene.numTiles * scene.tileTris)
+    return;
+  const uint32_t tile = slot / scene.tileTris, within = slot % scene.tileTris;
+  const double *src = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris + within;
+  float *dst = args.out + static_cast<size_t>(tile) * 13 * scene.tileTris + within;
+  double v[9];
+  for (int k = 0; k < 9; ++k) {
+    v[k] = src[static_cast<size_t>(k) * scene.tileTris];
+    dst[static_cast<size_t>(k) * scene.tileTris] = __double2float_rn(v[k]);
+  }
+  const bool padding = slot >= scene.numTriangles;
+  const double lenV0 = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const double lenE1 = sqrt(v[3] * v[3] + v[4] * v[4] + v[5] * v[5]);
+  const double lenE2 = sqrt(v[6] * v[6] + v[7] * v[7] + v[8] * v[8]);
+  // 2^-18 = 64 FP32 unit roundoffs (2^-24): |det32 - det| <= ~13u |e1||e2|,
+  // |X32 - X| <= ~16u (|o|+|v0|)|e2|, |Y32 - Y| <= ~18u (|o|+|v0|)|e1| by forward error analysis
+  // of the 24 operations on inputs rounded to FP32; the rest is safety margin, which also
+  // covers the rounding of the comparisons themselves.
+  const double c = 0x1p-18;
+  const double reach = args.originBound + lenV0;
+  const double ed = c * lenE1 * lenE2;
+  const double ex = c * lenE2 * reach;
+  const double ey = c * lenE1 * reach;
+  const double slack = 1.0 + 0x1p-10;
+  float fed = __double2float_ru(ed * slack);
+  float fkx = __double2float_ru(2.0 * ex * slack);
+  float fky = __double2float_ru(2.0 * ey * slack);
+  float fk3 = __double2float_ru((ed * (1.0 + 0x1p-20) + ex + ey) * slack);
+  if (padding) { // all-zero padding triangles: make stage 0 reject them outright
+    fed = -1.0f;
+    fkx = -1.0f;
+    fky = -1.0f;
+    fk3 = 0.0f;
+  }
+  dst[static_cast<size_t>(9) * scene.tileTris] = fed;
+  dst[static_cast<size_t>(10) * scene.tileTris] = fkx;
+  dst[static_cast<size_t>(11) * scene.tileTris] = fky;
+  dst[static_cast<size_t>(12) * scene.tileTris] = fk3;
+}
+
+// For every (ray, triangle): does stage 0 keep it, does the exact test accept it (with no
+// nearer-than limit), and is there any triangle the exact test accepts but stage 0 rejects?
+__global__ void auditStage0Kernel(const __grid_constant__ AuditArgs args) {
+  const DeviceScene &scene = args.scene;
+  const uint32_t ray = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long pairs = 0, kept = 0, accepted = 0, violations = 0;
+  if (ray < args.numRays) {
+    const V3 o = mk(args.rays[6 * ray + 0], args.rays[6 * ray + 1], args.rays[6 * ray + 2]);
+    const V3 d = mk(args.rays[6 * ray + 3], args.rays[6 * ray + 4], args.rays[6 * ray + 5]);
+    const Stage0Ray r{static_cast<float>(o.x), static_cast<float>(o.y), static_cast<float>(o.z),
+                      static_cast<float>(d.x), static_cast<float>(d.y), static_cast<float>(d.z)};
+    for (uint32_t index = 0; index < scene.numTriangles; ++index) {
+      const uint32_t tile = index / scene.tileTris, i = index % scene.tileTris;
+      const float *f = scene.triFilter + static_cast<size_t>(tile) * 13 * scene.tileTris + i;
+      const double *e = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris + i;
+      const uint32_t n = scene.tileTris;
+      const bool keep = stage0Keep(f[0], f[n], f[2 * n], f[3 * n], f[4 * n], f[5 * n], f[6 * n], f[7 * n],
+                                   f[8 * n], f[9 * n], f[10 * n], f[11 * n], f[12 * n], r);
+      Nearest best{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim};
+      testTriangle(mk(e[0], e[n], e[2 * n]), mk(e[3 * n], e[4 * n], e[5 * n]), mk(e[6 * n], e[7 * n], e[8 * n]),
+                   o, d, static_cast<int>(index), best);
+      const bool accept = best.prim != kNoPrim;
+      ++pairs;
+      kept += keep;
+      accepted += accept;
+      violations += accept && !keep;
+    }
+  }
+  atomicAdd(args.counters + 0, pairs);
+  atomicAdd(args.counters + 1, kept);
+  atomicAdd(args.counters + 2, accepted);
+  atomicAdd(args.counters + 3, violations);
 }
 
 // =============================================================================================
@@ -788,11 +880,12 @@ __global__ void fp64PeakKernel(double *sink, int iterations) {
 // Host-side launchers (called from ptb200_shim.cu).
 // =============================================================================================
 constexpr int kSequentialWarps = 2;
+constexpr int kDefaultKeyedConfig = 1;
 
-template <int kBlock, int kMinBlocks, bool kPrefilter>
-cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, size_t smemBytes, cudaStream_t stream,
-                              int *blocksLaunched) {
-  auto kernel = renderKeyedKernel<kBlock, kMinBlocks, kPrefilter>;
+template <int kBlock, int kMinBlocks, int kSweep>
+cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t stream) {
+  auto kernel = renderKeyedKernel<kBlock, kMinBlocks, kSweep>;
+  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep);
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smemBytes));
   if (err != cudaSuccess)
@@ -808,27 +901,33 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, size_t smemByte
   unsigned long long grid = static_cast<unsigned long long>(numSms) * perSm;
   if (wanted < grid)
     grid = wanted ? wanted : 1;
-  if (blocksLaunched)
-    *blocksLaunched = static_cast<int>(grid);
   kernel<<<static_cast<unsigned>(grid), kBlock, smemBytes, stream>>>(args);
   return cudaGetLastError();
 }
 
-cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, size_t smemBytes, cudaStream_t stream,
-                              int *blocksLaunched) {
-  // PTB200_KEYED_CONFIG selects (threads per CTA, min CTAs per SM, sweep variant) for
-  // tools/sweep_configs.py.  The default is what measured best on B200.
+// PTB200_KEYED_CONFIG = 10 * launchShape + sweepVariant selects the megakernel instantiation
+// (tools/sweep_configs.py).  Sweep variants: 0 one-stage FP64, 1 two-stage FP64 (prefilter +
+// exact), 2 FP32 stage 0 + exact.  Launch shapes: 0 = 256 threads x 2 CTAs/SM (128 registers),
+// 1 = 384 x 1 (168 registers), 2 = 256 x 3 (80 registers).
+static int keyedConfig() {
   static const int config = [] {
     const char *env = getenv("PTB200_KEYED_CONFIG");
-    return env ? atoi(env) : 0;
+    return env ? atoi(env) : kDefaultKeyedConfig;
   }();
-  switch (config) {
-  case 1: return launchKeyedConfig<256, 2, false>(args, numSms, smemBytes, stream, blocksLaunched); // one-stage sweep
-  case 2: return launchKeyedConfig<512, 1, true>(args, numSms, smemBytes, stream, blocksLaunched);
-  case 3: return launchKeyedConfig<384, 1, true>(args, numSms, smemBytes, stream, blocksLaunched);  // 168 regs
-  case 4: return launchKeyedConfig<128, 4, true>(args, numSms, smemBytes, stream, blocksLaunched);
-  case 5: return launchKeyedConfig<256, 3, true>(args, numSms, smemBytes, stream, blocksLaunched);  // 80 regs
-  default: return launchKeyedConfig<256, 2, true>(args, numSms, smemBytes, stream, blocksLaunched); // 128 regs
+  return config;
+}
+int keyedSweepVariant() { return keyedConfig() % 10; }
+
+cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, cudaStream_t stream) {
+  switch (keyedConfig()) {
+  case 0: return launchKeyedConfig<256, 2, 0>(args, numSms, stream);
+  case 1: return launchKeyedConfig<256, 2, 1>(args, numSms, stream);
+  case 2: return launchKeyedConfig<256, 2, 2>(args, numSms, stream);
+  case 11: return launchKeyedConfig<384, 1, 1>(args, numSms, stream);
+  case 12: return launchKeyedConfig<384, 1, 2>(args, numSms, stream);
+  case 21: return launchKeyedConfig<256, 3, 1>(args, numSms, stream);
+  case 22: return launchKeyedConfig<256, 3, 2>(args, numSms, stream);
+  default: return cudaErrorInvalidValue;
   }
 }
 
@@ -845,7 +944,21 @@ cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-cudaError_t launchIntersect(const IntersectArgs &args, size_t smemBytes, cudaStream_t stream) {
+cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream) {
+  const uint32_t slots = args.scene.numTiles * args.scene.tileTris;
+  if (slots == 0)
+    return cudaSuccess;
+  buildFilterKernel<<<(slots + 127) / 128, 128, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream) {
+  auditStage0Kernel<<<(args.numRays + 127) / 128, 128, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream) {
+  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, args.sweep);
   cudaError_t err = cudaFuncSetAttribute(intersectKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smemBytes));
   if (err != cudaSuccess)

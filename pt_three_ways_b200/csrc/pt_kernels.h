@@ -30,6 +30,8 @@ struct KeyedArgs {
   unsigned long long totalItems;   // ownPixels * passes of this batch
   int32_t seed, passBegin;         // pass s of the batch uses key seed + passBegin + s
   int32_t maxDepth, firstBounceU, firstBounceV, preview;
+  int32_t firstBounceUPow2, firstBounceVPow2; // strata counts are powers of two:
+  double invFirstBounceU, invFirstBounceV;    //   divide by multiplying with the exact reciprocal
   double *samples;                 // [passInBatch][ownPixel][3]
   unsigned long long *ticket;      // work counter, zeroed before launch
   unsigned long long *castCounter;
@@ -56,6 +58,20 @@ struct ReduceArgs {
   int32_t samplesAreFullFrame;     // sequential kernel writes whole frames
 };
 
+struct BuildFilterArgs {
+  DeviceScene scene;
+  float *out;                      // [numTiles][13][tileTris]
+  double originBound;              // >= |o| for every ray origin of the coming launch
+};
+
+struct AuditArgs {                 // test hook: stage 0 must never reject what the exact test accepts
+  DeviceScene scene;
+  const double *rays;
+  uint32_t numRays;
+  unsigned long long *counters;    // [0] (ray,triangle) pairs, [1] stage-0 survivors,
+                                   // [2] exact accepts, [3] VIOLATIONS: exact accept but stage-0 reject
+};
+
 struct IntersectArgs {
   DeviceScene scene;
   const double *rays;
@@ -64,15 +80,17 @@ struct IntersectArgs {
   int32_t which;                   // 0 intersect, 1 spheres only, 2 triangles only
   double nearerThan;
   int32_t warpCooperative;
-  int32_t prefilter;               // two-stage sweep (sweepTilePrefiltered)
+  int32_t sweep;                   // 0 one-stage, 1 two-stage FP64, 2 FP32 stage 0 + exact
 };
 
-size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles);
-cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, size_t smemBytes,
-                              cudaStream_t stream, int *blocksLaunched);
+size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep);
+int keyedSweepVariant();  // what PTB200_KEYED_CONFIG selects for the megakernel
+cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream);
+cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream);
+cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, cudaStream_t stream);
 cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream);
 cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream);
-cudaError_t launchIntersect(const IntersectArgs &args, size_t smemBytes, cudaStream_t stream);
+cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream);
 cudaError_t launchFp64Peak(double *sink, int iterations, int blocks, int threads,
                            cudaStream_t stream);
 

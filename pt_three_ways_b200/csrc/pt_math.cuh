@@ -150,8 +150,7 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 // Norm3::reflectance (src/math/Norm3.cpp:7-24).  rParallel is evaluated with the
 // rPerpendicular formula there, so (rPerp^2 + rPar^2)/2 == rPerp^2 exactly.
 __device__ __forceinline__ double reflectance(V3 normal, V3 incoming, double iorFrom,
-                                              double iorTo) {
-  const double iorRatio = ieeeDiv(iorFrom, iorTo);
+                                              double iorTo, double iorRatio /* iorFrom / iorTo */) {
   const double cosThetaI = -dot(normal, incoming);
   const double sinThetaTSquared = (iorRatio * iorRatio) * fma(-cosThetaI, cosThetaI, 1.0);
   if (sinThetaTSquared > 1)

@@ -72,6 +72,14 @@ H3 shadingNormal(H3 e1, H3 e2) {
   return hnormalised(H3{0.0 + face.x, 0.0 + face.y, 0.0 + face.z});
 }
 
+// OrthoNormalBasis::fromZ (OrthoNormalBasis.cpp:36-51) with the arithmetic of basisFromZ() in
+// pt_math.cuh, for the per-triangle bases stored next to the shading normal.
+void basisFromZ(H3 z, H3 &xx, H3 &yy) {
+  const H3 c = std::fabs(z.x) > 0.9999 ? H3{z.z, 0.0, -z.x} : H3{0.0, -z.z, z.y};
+  xx = hnormalised(c);
+  yy = hnormalised(hcross(z, xx));
+}
+
 template <typename T>
 struct DeviceBuffer {
   T *ptr{nullptr};
@@ -107,6 +115,10 @@ struct PtContext {
   DeviceBuffer<double4> spheres;
   DeviceBuffer<uint32_t> sphereMaterial;
   DeviceBuffer<double> materials;
+  DeviceBuffer<float> triFilter;
+  double sceneRadius{0};       // >= |p| for every vertex / sphere surface point
+  double filterOriginBound{-1}; // origin bound the current triFilter contents were built for
+  bool filterUsable{false};    // FP32 stage 0 allowed (coordinates comfortably inside FP32 range)
   DeviceBuffer<PtPixelDevice> accumulator;
   DeviceBuffer<double> samples;
   DeviceBuffer<unsigned long long> counters; // [0] ticket, [1] casts
@@ -171,7 +183,7 @@ void planTiles(uint32_t numTriangles, uint32_t &tileTris, uint32_t &numTiles) {
                  ? 1u
                  : static_cast<uint32_t>((bytes + kStreamTileBytes - 1) / kStreamTileBytes);
   tileTris = (numTriangles + numTiles - 1) / numTiles;
-  tileTris = (tileTris + 1u) & ~1u;
+  tileTris = (tileTris + 3u) & ~3u; // 16-byte loads of 2 doubles / 4 floats
   numTiles = (numTriangles + tileTris - 1) / tileTris;
 }
 
@@ -283,7 +295,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
 
   const size_t sweepDoubles = static_cast<size_t>(d.numTiles) * 9 * d.tileTris;
   std::vector<double> sweep(sweepDoubles, 0.0);
-  std::vector<double4> shade(scene->numTriangles);
+  std::vector<double4> shade(static_cast<size_t>(scene->numTriangles) * 4);
   for (uint32_t i = 0; i < scene->numTriangles; ++i) {
     const double *t = scene->triangleVertices + 9 * static_cast<size_t>(i);
     const H3 v0{t[0], t[1], t[2]}, v1{t[3], t[4], t[5]}, v2{t[6], t[7], t[8]};
@@ -294,19 +306,46 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
     for (int a = 0; a < 9; ++a)
       base[static_cast<size_t>(a) * d.tileTris] = values[a];
     const H3 n = shadingNormal(e1, e2);
-    shade[i] = make_double4(n.x, n.y, n.z, static_cast<double>(scene->triangleMaterial[i]));
+    H3 fx, fy, bx, by;
+    basisFromZ(n, fx, fy);
+    basisFromZ(H3{-n.x, -n.y, -n.z}, bx, by);
+    double4 *record = shade.data() + 4 * static_cast<size_t>(i);
+    record[0] = make_double4(n.x, n.y, n.z, static_cast<double>(scene->triangleMaterial[i]));
+    record[1] = make_double4(fx.x, fx.y, fx.z, fy.x);
+    record[2] = make_double4(fy.y, fy.z, bx.x, bx.y);
+    record[3] = make_double4(bx.z, by.x, by.y, by.z);
   }
   std::vector<double4> spheres(scene->numSpheres);
+  double radius = 0, longestEdge = 0;
   for (uint32_t i = 0; i < scene->numSpheres; ++i) {
     const double *s = scene->sphereCentreRadius + 4 * static_cast<size_t>(i);
     spheres[i] = make_double4(s[0], s[1], s[2], s[3] * s[3]); // Sphere.h:11
+    radius = std::max(radius, std::sqrt(s[0] * s[0] + s[1] * s[1] + s[2] * s[2]) + std::fabs(s[3]));
   }
+  for (uint32_t i = 0; i < scene->numTriangles; ++i) {
+    const double *t = scene->triangleVertices + 9 * static_cast<size_t>(i);
+    for (int k = 0; k < 3; ++k)
+      radius = std::max(radius, std::sqrt(t[3 * k] * t[3 * k] + t[3 * k + 1] * t[3 * k + 1] + t[3 * k + 2] * t[3 * k + 2]));
+    for (int k = 1; k < 3; ++k) {
+      const double ex = t[3 * k] - t[0], ey = t[3 * k + 1] - t[1], ez = t[3 * k + 2] - t[2];
+      longestEdge = std::max(longestEdge, std::sqrt(ex * ex + ey * ey + ez * ez));
+    }
+  }
+  ctx->sceneRadius = radius;
+  ctx->filterUsable = std::isfinite(radius) && radius < 1e6 && longestEdge < 1e6;
+  ctx->filterOriginBound = -1;
 
   PT_CUDA(ctx->triSweep.ensure(sweepDoubles));
   PT_CUDA(ctx->triShade.ensure(shade.size()));
+  PT_CUDA(ctx->triFilter.ensure(static_cast<size_t>(d.numTiles) * 13 * d.tileTris));
   PT_CUDA(ctx->spheres.ensure(spheres.size()));
   PT_CUDA(ctx->sphereMaterial.ensure(scene->numSpheres));
-  PT_CUDA(ctx->materials.ensure(static_cast<size_t>(scene->numMaterials) * 9));
+  PT_CUDA(ctx->materials.ensure(static_cast<size_t>(scene->numMaterials) * 10));
+  std::vector<double> materials(static_cast<size_t>(scene->numMaterials) * 10);
+  for (uint32_t i = 0; i < scene->numMaterials; ++i) {
+    std::memcpy(&materials[10 * static_cast<size_t>(i)], &scene->materials[i], 72);
+    materials[10 * static_cast<size_t>(i) + 9] = 1.0 / scene->materials[i].indexOfRefraction;
+  }
   if (sweepDoubles)
     PT_CUDA(cudaMemcpyAsync(ctx->triSweep.ptr, sweep.data(), sweepDoubles * 8, cudaMemcpyHostToDevice, ctx->stream));
   if (!shade.empty())
@@ -315,7 +354,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
     PT_CUDA(cudaMemcpyAsync(ctx->spheres.ptr, spheres.data(), spheres.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
     PT_CUDA(cudaMemcpyAsync(ctx->sphereMaterial.ptr, scene->sphereMaterial, scene->numSpheres * 4, cudaMemcpyHostToDevice, ctx->stream));
   }
-  PT_CUDA(cudaMemcpyAsync(ctx->materials.ptr, scene->materials, static_cast<size_t>(scene->numMaterials) * 72,
+  PT_CUDA(cudaMemcpyAsync(ctx->materials.ptr, materials.data(), materials.size() * 8,
                           cudaMemcpyHostToDevice, ctx->stream));
   PT_CUDA(cudaStreamSynchronize(ctx->stream)); // staging vectors go out of scope
   d.triSweep = ctx->triSweep.ptr;
@@ -323,11 +362,27 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   d.spheres = ctx->spheres.ptr;
   d.sphereMaterial = ctx->sphereMaterial.ptr;
   d.materials = ctx->materials.ptr;
+  d.triFilter = ctx->triFilter.ptr;
   d.environment[0] = scene->environment[0];
   d.environment[1] = scene->environment[1];
   d.environment[2] = scene->environment[2];
   ctx->scene = d;
   ctx->haveScene = true;
+  return PTB200_OK;
+}
+
+// (Re)builds the FP32 stage-0 arrays for ray origins within `originBound` of the world origin.
+static int ensureFilter(PtContext *ctx, double originBound, uint64_t *launches) {
+  if (ctx->filterOriginBound >= originBound)
+    return PTB200_OK;
+  BuildFilterArgs b{};
+  b.scene = ctx->scene;
+  b.out = ctx->triFilter.ptr;
+  b.originBound = originBound;
+  PT_CUDA(launchBuildFilter(b, ctx->stream));
+  ctx->filterOriginBound = originBound;
+  if (launches && ctx->scene.numTiles)
+    *launches += 1;
   return PTB200_OK;
 }
 
@@ -352,6 +407,17 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
     passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(opt.passesPerBatch));
   passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses));
   PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
+  if (!sequential && keyedSweepVariant() == 2) {
+    if (!ctx->filterUsable)
+      return fail(PTB200_EINVAL, "scene coordinates exceed the range the FP32 stage-0 sweep supports; "
+                                 "select a FP64 sweep (PTB200_KEYED_CONFIG=1)");
+    // Ray origins are the camera (centre + aperture disc) or points on primitives.
+    const double cameraReach = std::sqrt(camera->centre[0] * camera->centre[0] + camera->centre[1] * camera->centre[1] +
+                                         camera->centre[2] * camera->centre[2]) + std::fabs(camera->apertureRadius);
+    const double bound = std::max(ctx->sceneRadius, cameraReach) * (1.0 + 1e-6);
+    if (const int rc = ensureFilter(ctx, bound, launches))
+      return rc;
+  }
 
   for (int done = 0; done < numPasses;) {
     const int batch = static_cast<int>(std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses - done)));
@@ -393,11 +459,14 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.firstBounceU = params->firstBounceUSamples;
       a.firstBounceV = params->firstBounceVSamples;
       a.preview = params->preview;
+      a.firstBounceUPow2 = (a.firstBounceU & (a.firstBounceU - 1)) == 0;
+      a.firstBounceVPow2 = (a.firstBounceV & (a.firstBounceV - 1)) == 0;
+      a.invFirstBounceU = 1.0 / static_cast<double>(a.firstBounceU);
+      a.invFirstBounceV = 1.0 / static_cast<double>(a.firstBounceV);
       a.samples = ctx->samples.ptr;
       a.ticket = ctx->counters.ptr;
       a.castCounter = ctx->counters.ptr + 1;
-      const size_t smem = keyedSmemBytes(ctx->scene.numSpheres, ctx->scene.tileTris, ctx->scene.numTiles);
-      PT_CUDA(launchRenderKeyed(a, ctx->numSms, smem, ctx->stream, nullptr));
+      PT_CUDA(launchRenderKeyed(a, ctx->numSms, ctx->stream));
     }
     if (events) {
       PT_CUDA(cudaEventRecord(e1, ctx->stream));
@@ -641,8 +710,10 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
     return PTB200_OK;
   if (!rays || !out)
     return fail(PTB200_EINVAL, "null argument");
-  // Test hooks: bit 8 of `which` selects the warp-cooperative sweep of the sequential kernel,
-  // bit 9 the one-stage (no prefilter) per-lane sweep.
+  // Test hooks in `which`: bit 8 = the warp-cooperative sweep of the sequential kernel;
+  // bits 9-10 = per-lane sweep variant + 1 (0 -> default two-stage FP64); bit 11 = stage-0
+  // audit: `out` then receives four uint64 counters (pairs, stage-0 survivors, exact accepts,
+  // VIOLATIONS) instead of hits.
   const int32_t mode = which & 0xff;
   if (mode < 0 || mode > 2)
     return fail(PTB200_EINVAL, "which must be 0, 1 or 2");
@@ -669,9 +740,34 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
     a.which = mode;
     a.nearerThan = nearerThan;
     a.warpCooperative = (which & 0x100) ? 1 : 0;
-    a.prefilter = (which & 0x200) ? 0 : 1;
-    const size_t smem = keyedSmemBytes(ctx->scene.numSpheres, ctx->scene.tileTris, ctx->scene.numTiles);
-    PT_CUDA(launchIntersect(a, smem, ctx->stream));
+    const int variant = (which >> 9) & 3;
+    a.sweep = variant ? variant - 1 : 1;
+    const bool audit = (which & 0x800) != 0;
+    if (a.sweep == 2 || audit) {
+      if (!ctx->filterUsable)
+        return fail(PTB200_EINVAL, "scene outside the FP32 stage-0 range");
+      double bound = ctx->sceneRadius;
+      for (uint32_t i = 0; i < numRays; ++i)
+        bound = std::max(bound, std::sqrt(rays[6 * i] * rays[6 * i] + rays[6 * i + 1] * rays[6 * i + 1] +
+                                          rays[6 * i + 2] * rays[6 * i + 2]));
+      if (const int rc2 = ensureFilter(ctx, bound * (1.0 + 1e-6), nullptr))
+        return rc2;
+    }
+    if (audit) {
+      DeviceBuffer<unsigned long long> counters;
+      PT_CUDA(counters.ensure(4));
+      PT_CUDA(cudaMemsetAsync(counters.ptr, 0, 32, ctx->stream));
+      AuditArgs au{};
+      au.scene = ctx->scene;
+      au.rays = dRays.ptr;
+      au.numRays = numRays;
+      au.counters = counters.ptr;
+      PT_CUDA(launchAuditStage0(au, ctx->stream));
+      PT_CUDA(cudaMemcpyAsync(out, counters.ptr, 32, cudaMemcpyDeviceToHost, ctx->stream));
+      PT_CUDA(cudaStreamSynchronize(ctx->stream));
+      return PTB200_OK;
+    }
+    PT_CUDA(launchIntersect(a, ctx->stream));
     PT_CUDA(cudaMemcpyAsync(out, dOut.ptr, static_cast<size_t>(numRays) * sizeof(PtHit), cudaMemcpyDeviceToHost, ctx->stream));
     PT_CUDA(cudaStreamSynchronize(ctx->stream));
     return PTB200_OK;

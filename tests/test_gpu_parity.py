@@ -53,18 +53,36 @@ def assert_hits_equal(got, want):
 
 
 @pytest.mark.parametrize("name", SCENE_NAMES)
-@pytest.mark.parametrize("sweep", ["two-stage", "one-stage", "warp-cooperative"])
+@pytest.mark.parametrize("sweep", ["two-stage", "one-stage", "fp32-stage0", "warp-cooperative"])
 def test_intersect_matches_oracle(name, sweep, scenes, oracle, capi):
-    """All three sweep implementations (the megakernel's prefilter + exact two-stage sweep, the
-    plain one-stage sweep, the sequential kernel's lane-strided sweep) return the oracle's
-    nearest hit bit for bit."""
+    """Every sweep implementation (two-stage FP64 prefilter + exact, plain one-stage, FP32 stage 0 +
+    exact, the sequential kernel's lane-strided sweep) returns the oracle's nearest hit bit for bit."""
     scene = scenes[name]
     rays = random_rays(scene, 3000 if name != "ce" else 1500, seed=sum(map(ord, name)))
     want = oracle.OracleScene(scene).intersect(rays)
-    got = capi.intersect(scene, rays, warp_cooperative=sweep == "warp-cooperative",
-                         one_stage=sweep == "one-stage")
+    variant = {"two-stage": capi.SWEEP_TWO_STAGE_FP64, "one-stage": capi.SWEEP_ONE_STAGE,
+               "fp32-stage0": capi.SWEEP_FP32_STAGE0}.get(sweep)
+    got = capi.intersect(scene, rays, warp_cooperative=sweep == "warp-cooperative", sweep=variant)
     assert (want[:, 0] != 0).sum() > 100
     assert_hits_equal(got, want)
+
+
+@pytest.mark.parametrize("name", [n for n in SCENE_NAMES if n not in ("single-sphere", "multi-sphere")])
+def test_fp32_stage0_never_rejects_an_exact_hit(name, scenes, capi):
+    """The conservative FP32 filter audited on every (ray, triangle) pair: zero pairs may be
+    accepted by the exact FP64 test yet rejected by stage 0, and the filter must be selective."""
+    scene = scenes[name]
+    n = 20000 if scene.num_triangles < 100 else 1500
+    rays = random_rays(scene, n, seed=1234)
+    # grazing rays: directions almost inside triangle planes stress the |det| ~ 0 branch
+    tri = scene.triangle_vertices[np.random.default_rng(5).integers(0, scene.num_triangles, n // 4)].reshape(-1, 3, 3)
+    inplane = tri[:, 1] - tri[:, 0] + 1e-7 * (tri[:, 2] - tri[:, 0])
+    rays[: n // 4, 3:] = inplane / np.linalg.norm(inplane, axis=1, keepdims=True)
+    res = capi.audit_stage0(scene, rays)
+    assert res["pairs"] == n * scene.num_triangles
+    assert res["violations"] == 0
+    assert res["accepts"] > 0 and res["survivors"] >= res["accepts"]
+    assert res["survivors"] < 0.5 * res["pairs"]
 
 
 @pytest.mark.parametrize("which", [1, 2])
@@ -212,8 +230,8 @@ def test_progress_callback_runs_on_calling_thread_with_partial_frames(scenes, ca
 
 
 def test_one_stage_sweep_config_renders_identically(scenes, tmp_path):
-    """PTB200_KEYED_CONFIG=1 (plain one-stage sweep) and the default two-stage sweep must give
-    the same framebuffer bit for bit."""
+    """Every megakernel instantiation (sweep variant x launch shape, PTB200_KEYED_CONFIG) must give
+    the same framebuffer and cast count bit for bit."""
     import os
     import subprocess
     import sys
@@ -225,11 +243,11 @@ def test_one_stage_sweep_config_renders_identically(scenes, tmp_path):
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
                 root, os.path.join(root, "tests/golden/scenes/suzanne.ptscene"))
     outs = []
-    for config in ("0", "1", "3"):
+    for config in ("1", "0", "2", "11", "22"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
         assert res.returncode == 0, res.stderr[-1500:]
         outs.append((np.load(out), res.stdout.strip()))
-    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
-    assert np.array_equal(outs[0][0], outs[2][0])
+    for other in outs[1:]:
+        assert np.array_equal(outs[0][0], other[0]) and outs[0][1] == other[1]

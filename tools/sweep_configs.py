@@ -27,7 +27,7 @@ for _ in range(3):
         best = st
 ms = best["sweep_kernel_ms"]
 print(json.dumps(dict(scene=%(scene)r, w=w, h=h, spp=spp, mode=mode,
-    config=os.environ.get("PTB200_KEYED_CONFIG", "0"), ms=ms,
+    config=os.environ.get("PTB200_KEYED_CONFIG", "default"), ms=ms,
     msamples_s=best["samples"] / ms / 1e3, mcasts_s=best["casts"] / ms / 1e3,
     casts_per_sample=best["casts"] / best["samples"],
     logical_gbs=best["casts"] * scene.sweep_bytes() / ms / 1e6,
@@ -47,7 +47,7 @@ if __name__ == "__main__":
     w = int(sys.argv[2]) if len(sys.argv) > 2 else 640
     h = int(sys.argv[3]) if len(sys.argv) > 3 else 480
     spp = int(sys.argv[4]) if len(sys.argv) > 4 else 32
-    configs = [int(c) for c in os.environ.get("SWEEP_CONFIGS", "0,1,2,3,4,5,6").split(",")]
+    configs = [int(c) for c in os.environ.get("SWEEP_CONFIGS", "1,0,2,11,12,21,22").split(",")]
     for config in configs:
         run(scene, w, h, spp, 0, config)
     if os.environ.get("SWEEP_SEQUENTIAL", "1") == "1":
