@@ -184,7 +184,7 @@ def render(scene, camera18, params: PtRenderParams, options: PtRenderOptions | N
     return out, _stats_dict(st)
 
 
-SWEEP_ONE_STAGE, SWEEP_TWO_STAGE_FP64, SWEEP_FP32_STAGE0 = 0, 1, 2
+SWEEP_ONE_STAGE, SWEEP_TWO_STAGE_FP64, SWEEP_FP32_STAGE0, SWEEP_FP32X2_STAGE0 = 0, 1, 2, 3
 
 
 def intersect(scene, rays, which=0, nearer_than=float("inf"), device=0, warp_cooperative=False,
@@ -204,7 +204,7 @@ def audit_stage0(scene, rays, device=0) -> dict:
     m = scene if isinstance(scene, MarshalledScene) else MarshalledScene(scene)
     rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
     out = np.zeros(max(1, rays.shape[0]), dtype=HIT_DTYPE)
-    _check(lib().ptb200_intersect(C.byref(m.abi), device, 0x800, float("inf"), rays.shape[0],
+    _check(lib().ptb200_intersect(C.byref(m.abi), device, 0x1000, float("inf"), rays.shape[0],
                                   rays.ctypes.data, out.ctypes.data))
     counters = out.view(np.uint64)[:4]
     return dict(pairs=int(counters[0]), survivors=int(counters[1]), accepts=int(counters[2]),

@@ -236,14 +236,51 @@ __device__ __forceinline__ bool stage0Keep(float v0x, float v0y, float v0z, floa
   return (adet <= ed) | !certain;
 }
 
+// The same test for TWO triangles at once in the packed FP32x2 datapath (FFMA2/FMUL2/FADD2,
+// new on sm_100): .x holds triangle i, .y triangle i+1.  Returns bit 0 / bit 1.
+struct Stage0Ray2 {
+  float2 ox, oy, oz, dx, dy, dz; // each component duplicated into both halves
+};
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ unsigned stage0Keep2(float2 v0x, float2 v0y, float2 v0z, float2 e1x,
+                                                float2 e1y, float2 e1z, float2 e2x, float2 e2y,
+                                                float2 e2z, float2 ed, float2 kx, float2 ky,
+                                                float2 k3, const Stage0Ray2 &r) {
+  const float2 px = __ffma2_rn(r.dy, e2z, neg2(__fmul2_rn(r.dz, e2y)));
+  const float2 py = __ffma2_rn(r.dz, e2x, neg2(__fmul2_rn(r.dx, e2z)));
+  const float2 pz = __ffma2_rn(r.dx, e2y, neg2(__fmul2_rn(r.dy, e2x)));
+  const float2 det = __ffma2_rn(e1z, pz, __ffma2_rn(e1y, py, __fmul2_rn(e1x, px)));
+  const float2 tx = __fadd2_rn(r.ox, neg2(v0x)), ty = __fadd2_rn(r.oy, neg2(v0y)),
+               tz = __fadd2_rn(r.oz, neg2(v0z));
+  const float2 x = __ffma2_rn(tz, pz, __ffma2_rn(ty, py, __fmul2_rn(tx, px)));
+  const float2 qx = __ffma2_rn(ty, e1z, neg2(__fmul2_rn(tz, e1y)));
+  const float2 qy = __ffma2_rn(tz, e1x, neg2(__fmul2_rn(tx, e1z)));
+  const float2 qz = __ffma2_rn(tx, e1y, neg2(__fmul2_rn(ty, e1x)));
+  const float2 y = __ffma2_rn(r.dz, qz, __ffma2_rn(r.dy, qy, __fmul2_rn(r.dx, qx)));
+  const uint32_t signA = __float_as_uint(det.x) & 0x80000000u, signB = __float_as_uint(det.y) & 0x80000000u;
+  const float2 xs = make_float2(__uint_as_float(__float_as_uint(x.x) ^ signA), __uint_as_float(__float_as_uint(x.y) ^ signB));
+  const float2 ys = make_float2(__uint_as_float(__float_as_uint(y.x) ^ signA), __uint_as_float(__float_as_uint(y.y) ^ signB));
+  const float2 adet = make_float2(fabsf(det.x), fabsf(det.y));
+  const float2 sum = __fadd2_rn(xs, ys);
+  const float2 bound = __ffma2_rn(adet, make_float2(1.0f + 0x1p-20f, 1.0f + 0x1p-20f), k3);
+  const bool certainA = (xs.x < -kx.x) | (ys.x < -ky.x) | (sum.x > bound.x);
+  const bool certainB = (xs.y < -kx.y) | (ys.y < -ky.y) | (sum.y > bound.y);
+  const bool keepA = (adet.x <= ed.x) | !certainA;
+  const bool keepB = (adet.y <= ed.y) | !certainB;
+  return (keepA ? 1u : 0u) | (keepB ? 2u : 0u);
+}
+
 // `filter` is the FP32 tile in shared memory ([13][tileTris]); `exact` the same tile's FP64
 // sweep data in global memory ([9][tileTris]).  count is a multiple of 4.
+template <bool kPacked>
 __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter,
                                                 const double *__restrict__ exact, int tileTris,
                                                 int count, int firstIndex, V3 o, V3 d,
                                                 Nearest &best) {
   const Stage0Ray r{static_cast<float>(o.x), static_cast<float>(o.y), static_cast<float>(o.z),
                     static_cast<float>(d.x), static_cast<float>(d.y), static_cast<float>(d.z)};
+  const Stage0Ray2 r2{make_float2(r.ox, r.ox), make_float2(r.oy, r.oy), make_float2(r.oz, r.oz),
+                      make_float2(r.dx, r.dx), make_float2(r.dy, r.dy), make_float2(r.dz, r.dz)};
 #pragma unroll 1
   for (int chunk = 0; chunk < count; chunk += 64) {
     const int chunkEnd = min(count, chunk + 64);
@@ -254,7 +291,18 @@ __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter
 #pragma unroll
       for (int k = 0; k < 13; ++k)
         a[k] = *reinterpret_cast<const float4 *>(filter + k * tileTris + i);
-      const unsigned keep =
+      unsigned keep;
+      if (kPacked) {
+#define PT_LO(k) make_float2(a[k].x, a[k].y)
+#define PT_HI(k) make_float2(a[k].z, a[k].w)
+        keep = stage0Keep2(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6), PT_LO(7),
+                           PT_LO(8), PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), r2) |
+               (stage0Keep2(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6), PT_HI(7),
+                            PT_HI(8), PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), r2) << 2);
+#undef PT_LO
+#undef PT_HI
+      } else
+      keep =
           (stage0Keep(a[0].x, a[1].x, a[2].x, a[3].x, a[4].x, a[5].x, a[6].x, a[7].x, a[8].x, a[9].x, a[10].x, a[11].x, a[12].x, r) ? 1u : 0u) |
           (stage0Keep(a[0].y, a[1].y, a[2].y, a[3].y, a[4].y, a[5].y, a[6].y, a[7].y, a[8].y, a[9].y, a[10].y, a[11].y, a[12].y, r) ? 2u : 0u) |
           (stage0Keep(a[0].z, a[1].z, a[2].z, a[3].z, a[4].z, a[5].z, a[6].z, a[7].z, a[8].z, a[9].z, a[10].z, a[11].z, a[12].z, r) ? 4u : 0u) |

@@ -33,12 +33,22 @@ __host__ __device__ inline uint32_t smemTileOffset(uint32_t numSpheres) {
 constexpr uint32_t kExactBytesPerTriangle = 72;  // 9 doubles
 constexpr uint32_t kFilterBytesPerTriangle = 52; // 13 floats
 __host__ __device__ inline uint32_t sweepBytesPerTriangle(int sweep) {
-  return sweep == 2 ? kFilterBytesPerTriangle : kExactBytesPerTriangle;
+  return sweep >= 2 ? kFilterBytesPerTriangle : kExactBytesPerTriangle;
 }
 
-__host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep) {
-  const size_t tileBytes = static_cast<size_t>(tileTris) * sweepBytesPerTriangle(sweep);
-  return smemTileOffset(numSpheres) + tileBytes * (numTiles > 1 ? 2 : 1);
+__host__ __device__ inline uint32_t smemAfterTiles(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles,
+                                                   int sweep) {
+  return smemTileOffset(numSpheres) + tileTris * sweepBytesPerTriangle(sweep) * (numTiles > 1 ? 2u : 1u);
+}
+
+// The megakernel additionally parks each thread's primary-hit Surface (16 doubles) in shared
+// memory between the strata of a sample, [component][thread] so consecutive threads hit
+// consecutive banks; that keeps ~32 registers per thread free for a third resident CTA.
+constexpr uint32_t kPrimaryDoubles = 16;
+__host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
+                               uint32_t threadsForPrimarySlots) {
+  return smemAfterTiles(numSpheres, tileTris, numTiles, sweep) +
+         static_cast<size_t>(threadsForPrimarySlots) * kPrimaryDoubles * sizeof(double);
 }
 
 // Streams tiles cyclically (0,1,..,n-1,0,1,..) through two buffers with TMA bulk copies.
@@ -99,7 +109,7 @@ struct TileStream {
 __device__ __forceinline__ TileStream makeTileStream(unsigned char *smemBase, const DeviceScene &scene,
                                                      int sweep) {
   return TileStream{smemBase,
-                    sweep == 2 ? reinterpret_cast<const unsigned char *>(scene.triFilter)
+                    sweep >= 2 ? reinterpret_cast<const unsigned char *>(scene.triFilter)
                                : reinterpret_cast<const unsigned char *>(scene.triSweep),
                     scene.tileTris * sweepBytesPerTriangle(sweep), scene.numTiles,
                     smemTileOffset(scene.numSpheres), 0};
@@ -111,8 +121,8 @@ __device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const 
                                                 uint32_t tileIndex, V3 o, V3 d, Nearest &best) {
   const int tileTris = static_cast<int>(scene.tileTris);
   const int first = static_cast<int>(tileIndex * scene.tileTris);
-  if (kSweep == 2)
-    sweepTileStage0(reinterpret_cast<const float *>(tile),
+  if (kSweep >= 2)
+    sweepTileStage0<kSweep == 3>(reinterpret_cast<const float *>(tile),
                     scene.triSweep + static_cast<size_t>(tileIndex) * 9 * scene.tileTris, tileTris, tileTris,
                     first, o, d, best);
   else if (kSweep == 1)
@@ -191,7 +201,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   uint32_t key0 = 0;
   V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
   int depth = 0;                 // depth of the ray in flight
-  Surface primary{};             // the camera ray's hit, alive across its numSub sub-paths
+  // The camera ray's hit stays alive across its numSub sub-paths: in shared memory.
+  double *const primarySlot = reinterpret_cast<double *>(smemRaw + smemAfterTiles(scene.numSpheres, scene.tileTris,
+                                                                                  scene.numTiles, kSweep)) + threadIdx.x;
+  uint32_t primaryMaterial = 0;
   bool primarySpecular = false;
   int subPath = 0;
   V3 acc = mk(0, 0, 0);
@@ -305,7 +318,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       surface.reflectivity = hitReflectivity(materialOf(scene, hit.material), hit, direction);
       hitBasis(scene, hit, surface.basisX, surface.basisY);
       if (depth == 0) {
-        primary = surface;
+        const double values[kPrimaryDoubles] = {
+            surface.position.x, surface.position.y, surface.position.z, surface.normal.x, surface.normal.y,
+            surface.normal.z, surface.incoming.x, surface.incoming.y, surface.incoming.z, surface.basisX.x,
+            surface.basisX.y, surface.basisX.z, surface.basisY.x, surface.basisY.y, surface.basisY.z,
+            surface.reflectivity};
+#pragma unroll
+        for (uint32_t c = 0; c < kPrimaryDoubles; ++c)
+          primarySlot[c * kBlock] = values[c];
+        primaryMaterial = surface.material;
         acc = mk(0, 0, 0);
         subPath = 0;
       }
@@ -329,7 +350,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         // primary hit's own term, in the reference's summation order
         for (int level = depth - 1; level >= 1; --level)
           incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
-        acc = add(acc, shadeTerm(materialOf(scene, primary.material), primarySpecular, incoming));
+        acc = add(acc, shadeTerm(materialOf(scene, primaryMaterial), primarySpecular, incoming));
         ++subPath;
         if (subPath >= numSub) {
           colour = scale(acc, invNumSub); // Scene.cpp:178
@@ -351,8 +372,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     // ---- 4. ONE bounce site (Scene.cpp:155-175) ----
     if (bounce) {
       const bool fromPrimary = depth == 0;
-      if (fromPrimary)
-        surface = primary;
+      if (fromPrimary && !needSurface) { // a later stratum: reload what the camera hit stored
+        surface.position = mk(primarySlot[0 * kBlock], primarySlot[1 * kBlock], primarySlot[2 * kBlock]);
+        surface.normal = mk(primarySlot[3 * kBlock], primarySlot[4 * kBlock], primarySlot[5 * kBlock]);
+        surface.incoming = mk(primarySlot[6 * kBlock], primarySlot[7 * kBlock], primarySlot[8 * kBlock]);
+        surface.basisX = mk(primarySlot[9 * kBlock], primarySlot[10 * kBlock], primarySlot[11 * kBlock]);
+        surface.basisY = mk(primarySlot[12 * kBlock], primarySlot[13 * kBlock], primarySlot[14 * kBlock]);
+        surface.reflectivity = primarySlot[15 * kBlock];
+        surface.material = primaryMaterial;
+      }
       double ru, rv, rp;
       KeyedDraws{key0}.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
       double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
@@ -744,7 +772,9 @@ __global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
     if (args.which != 1) {
       for (uint32_t j = 0; j < scene.numTiles; ++j) {
         const unsigned char *tile = stream.acquire();
-        if (args.sweep == 2)
+        if (args.sweep == 3)
+          sweepStagedTile<3>(scene, tile, j, o, d, best);
+        else if (args.sweep == 2)
           sweepStagedTile<2>(scene, tile, j, o, d, best);
         else if (args.sweep == 1)
           sweepStagedTile<1>(scene, tile, j, o, d, best);
@@ -885,7 +915,7 @@ constexpr int kDefaultKeyedConfig = 1;
 template <int kBlock, int kMinBlocks, int kSweep>
 cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t stream) {
   auto kernel = renderKeyedKernel<kBlock, kMinBlocks, kSweep>;
-  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep);
+  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep, kBlock);
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smemBytes));
   if (err != cudaSuccess)
@@ -907,7 +937,7 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
 
 // PTB200_KEYED_CONFIG = 10 * launchShape + sweepVariant selects the megakernel instantiation
 // (tools/sweep_configs.py).  Sweep variants: 0 one-stage FP64, 1 two-stage FP64 (prefilter +
-// exact), 2 FP32 stage 0 + exact.  Launch shapes: 0 = 256 threads x 2 CTAs/SM (128 registers),
+// exact), 2 FP32 stage 0 + exact, 3 the same with the packed FP32x2 datapath (FFMA2).  Launch shapes: 0 = 256 threads x 2 CTAs/SM (128 registers),
 // 1 = 384 x 1 (168 registers), 2 = 256 x 3 (80 registers).
 static int keyedConfig() {
   static const int config = [] {
@@ -923,9 +953,16 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, cudaStream_t st
   case 0: return launchKeyedConfig<256, 2, 0>(args, numSms, stream);
   case 1: return launchKeyedConfig<256, 2, 1>(args, numSms, stream);
   case 2: return launchKeyedConfig<256, 2, 2>(args, numSms, stream);
+  case 3: return launchKeyedConfig<256, 2, 3>(args, numSms, stream);
+  case 13: return launchKeyedConfig<384, 1, 3>(args, numSms, stream);
+  case 23: return launchKeyedConfig<256, 3, 3>(args, numSms, stream);
   case 11: return launchKeyedConfig<384, 1, 1>(args, numSms, stream);
   case 12: return launchKeyedConfig<384, 1, 2>(args, numSms, stream);
   case 21: return launchKeyedConfig<256, 3, 1>(args, numSms, stream);
+  case 31: return launchKeyedConfig<192, 4, 1>(args, numSms, stream);
+  case 33: return launchKeyedConfig<192, 4, 3>(args, numSms, stream);
+  case 41: return launchKeyedConfig<128, 5, 1>(args, numSms, stream);
+  case 43: return launchKeyedConfig<128, 5, 3>(args, numSms, stream);
   case 22: return launchKeyedConfig<256, 3, 2>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
@@ -958,7 +995,7 @@ cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream) {
 }
 
 cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream) {
-  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, args.sweep);
+  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, args.sweep, 0);
   cudaError_t err = cudaFuncSetAttribute(intersectKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smemBytes));
   if (err != cudaSuccess)

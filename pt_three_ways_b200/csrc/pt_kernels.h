@@ -83,7 +83,8 @@ struct IntersectArgs {
   int32_t sweep;                   // 0 one-stage, 1 two-stage FP64, 2 FP32 stage 0 + exact
 };
 
-size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep);
+size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
+                      uint32_t threadsForPrimarySlots);
 int keyedSweepVariant();  // what PTB200_KEYED_CONFIG selects for the megakernel
 cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream);
 cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream);

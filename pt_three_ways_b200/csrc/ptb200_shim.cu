@@ -407,7 +407,7 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
     passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(opt.passesPerBatch));
   passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses));
   PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
-  if (!sequential && keyedSweepVariant() == 2) {
+  if (!sequential && keyedSweepVariant() >= 2) {
     if (!ctx->filterUsable)
       return fail(PTB200_EINVAL, "scene coordinates exceed the range the FP32 stage-0 sweep supports; "
                                  "select a FP64 sweep (PTB200_KEYED_CONFIG=1)");
@@ -711,7 +711,7 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
   if (!rays || !out)
     return fail(PTB200_EINVAL, "null argument");
   // Test hooks in `which`: bit 8 = the warp-cooperative sweep of the sequential kernel;
-  // bits 9-10 = per-lane sweep variant + 1 (0 -> default two-stage FP64); bit 11 = stage-0
+  // bits 9-11 = per-lane sweep variant + 1 (0 -> default two-stage FP64); bit 12 = stage-0
   // audit: `out` then receives four uint64 counters (pairs, stage-0 survivors, exact accepts,
   // VIOLATIONS) instead of hits.
   const int32_t mode = which & 0xff;
@@ -740,10 +740,10 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
     a.which = mode;
     a.nearerThan = nearerThan;
     a.warpCooperative = (which & 0x100) ? 1 : 0;
-    const int variant = (which >> 9) & 3;
+    const int variant = (which >> 9) & 7;
     a.sweep = variant ? variant - 1 : 1;
-    const bool audit = (which & 0x800) != 0;
-    if (a.sweep == 2 || audit) {
+    const bool audit = (which & 0x1000) != 0;
+    if (a.sweep >= 2 || audit) {
       if (!ctx->filterUsable)
         return fail(PTB200_EINVAL, "scene outside the FP32 stage-0 range");
       double bound = ctx->sceneRadius;
