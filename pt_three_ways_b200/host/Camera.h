@@ -46,6 +46,13 @@ public:
   }
 
   [[nodiscard]] const PtCamera &abi() const noexcept { return abi_; }
+
+  // A camera whose 18 doubles are already known (e.g. stored next to a scene fixture).
+  static Camera fromAbi(const PtCamera &state) {
+    Camera camera(Vec3(0, 0, 0), Vec3(0, 0, 1), Vec3(0, 1, 0).normalised(), 1, 1, 40.0);
+    camera.abi_ = state;
+    return camera;
+  }
 };
 
 } // namespace ptb200

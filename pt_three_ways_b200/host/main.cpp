@@ -1,7 +1,9 @@
 // pt_b200 — command-line driver with the reference CLI's flags (src/main/main.cpp:382-404):
 //   -w/--width -h/--height --max-cpus --spp --first-bounce-u --first-bounce-v --max-depth
 //   --seed --preview --save-every --way --scene --raw <output>
-// plus backend flags:  --rng keyed|exact   --gpus N (0 = all)   --scenes DIR   --device K.
+// plus backend flags:  --rng keyed|exact   --gpus N (0 = all)   --scenes DIR   --device K
+//   --ptscene FILE (a PTSCENE2 fixture instead of --scene: the reference loader's own output,
+//   usable where the OBJ files are not available).
 // Scene building, OBJ/MTL loading, the framebuffer and the PNG/raw writers are host C++ here
 // as they are in the reference; render() goes to the GPU through the C ABI.
 #include "ArrayOutput.h"
@@ -12,6 +14,7 @@
 
 #include <chrono>
 #include <cstdlib>
+#include <fstream>
 #include <functional>
 #include <iostream>
 #include <random>
@@ -38,6 +41,51 @@ void savePng(const ArrayOutput &output, const std::string &name) {
   }
 }
 
+// Reads a PTSCENE2 fixture (layout: pt_three_ways_b200/scenefile.py) through the SceneBuilder
+// calls; the stored camera is the recipe's for 64x48 and only three fields depend on the size.
+Camera loadPtScene(const std::string &path, Scene &scene, int width, int height) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in)
+    throw std::runtime_error("Unable to open " + path);
+  char magic[8];
+  uint32_t counts[4];
+  double env[3];
+  in.read(magic, 8);
+  in.read(reinterpret_cast<char *>(counts), sizeof counts);
+  in.read(reinterpret_cast<char *>(env), sizeof env);
+  if (!in || std::string(magic, 8) != "PTSCENE2")
+    throw std::runtime_error("Bad file " + path + " : not a PTSCENE2 scene");
+  std::vector<double> tri(static_cast<size_t>(counts[0]) * 9), sph(static_cast<size_t>(counts[1]) * 4),
+      mats(static_cast<size_t>(counts[2]) * 9);
+  std::vector<uint32_t> triMat(counts[0]), sphMat(counts[1]);
+  in.read(reinterpret_cast<char *>(tri.data()), static_cast<std::streamsize>(tri.size() * 8));
+  in.read(reinterpret_cast<char *>(triMat.data()), static_cast<std::streamsize>(triMat.size() * 4));
+  in.read(reinterpret_cast<char *>(sph.data()), static_cast<std::streamsize>(sph.size() * 8));
+  in.read(reinterpret_cast<char *>(sphMat.data()), static_cast<std::streamsize>(sphMat.size() * 4));
+  in.read(reinterpret_cast<char *>(mats.data()), static_cast<std::streamsize>(mats.size() * 8));
+  PtCamera cam{};
+  in.read(reinterpret_cast<char *>(&cam), sizeof cam);
+  if (!in)
+    throw std::runtime_error("Bad file " + path + " : truncated");
+  auto material = [&](uint32_t i) {
+    const double *m = &mats[9 * static_cast<size_t>(i)];
+    return MaterialSpec{Vec3(m[0], m[1], m[2]), Vec3(m[3], m[4], m[5]), m[6], m[7], m[8]};
+  };
+  for (uint32_t i = 0; i < counts[0]; ++i) {
+    const double *t = &tri[9 * static_cast<size_t>(i)];
+    scene.addTriangle(Vec3(t[0], t[1], t[2]), Vec3(t[3], t[4], t[5]), Vec3(t[6], t[7], t[8]), material(triMat[i]));
+  }
+  for (uint32_t i = 0; i < counts[1]; ++i) {
+    const double *s = &sph[4 * static_cast<size_t>(i)];
+    scene.addSphere(Vec3(s[0], s[1], s[2]), s[3], material(sphMat[i]));
+  }
+  scene.setEnvironmentColour(Vec3(env[0], env[1], env[2]));
+  cam.aspectRatio = static_cast<double>(width) / height; // Camera.h:43,46
+  cam.reciprocalHeight = 1.0 / height;
+  cam.reciprocalWidth = 1.0 / width;
+  return Camera::fromAbi(cam);
+}
+
 int usage(const char *argv0) {
   std::cerr << "usage: " << argv0
             << " [-w W] [-h H] [--spp N] [--max-cpus N] [--first-bounce-u N] [--first-bounce-v N]\n"
@@ -59,6 +107,7 @@ int main(int argc, const char *argv[]) {
   std::string sceneName = "cornell";
   std::string scenesDir = "scenes";
   std::string rng = "keyed";
+  std::string ptsceneFile;
   std::string outputName;
 
   for (int i = 1; i < argc; ++i) {
@@ -87,6 +136,7 @@ int main(int argc, const char *argv[]) {
     else if (arg == "--gpus") gpus = std::stoi(value());
     else if (arg == "--device") device = std::stoi(value());
     else if (arg == "--scenes") scenesDir = value();
+    else if (arg == "--ptscene") ptsceneFile = value();
     else if (arg == "--help" || arg == "-?") return usage(argv[0]);
     else if (!arg.empty() && arg[0] == '-') {
       std::cerr << "Error in command line: unknown option " << arg << '\n';
@@ -128,8 +178,10 @@ int main(int argc, const char *argv[]) {
 
     HostApi api(scenesDir);
     Scene scene;
-    Camera camera = SceneRecipes<HostApi>::create(api, scene, sceneName, renderParams.width,
-                                                  renderParams.height);
+    Camera camera = ptsceneFile.empty()
+                        ? SceneRecipes<HostApi>::create(api, scene, sceneName, renderParams.width,
+                                                        renderParams.height)
+                        : loadPtScene(ptsceneFile, scene, renderParams.width, renderParams.height);
     std::cout << "Scene contains " << scene.numTriangles() << " triangles and "
               << scene.numSpheres() << " spheres.\n"; // main.cpp:320-323
     scene.setRngMode(rng == "exact" ? PTB200_RNG_MT19937_SEQUENTIAL : PTB200_RNG_KEYED_PHILOX);

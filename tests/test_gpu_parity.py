@@ -251,3 +251,30 @@ def test_one_stage_sweep_config_renders_identically(scenes, tmp_path):
         outs.append((np.load(out), res.stdout.strip()))
     for other in outs[1:]:
         assert np.array_equal(outs[0][0], other[0]) and outs[0][1] == other[1]
+
+
+def test_cpp_host_adaptor_and_cli_render_identically(scenes, capi, tmp_path):
+    """The C++ host side (ptb200::Scene adaptor + CLI driver with the reference's flags) drives
+    the same C ABI: its raw output equals the ctypes render of the same scene, bit for bit."""
+    import os
+    import subprocess
+    from oracle import oracle_binding as ob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "pt_three_ways_b200", "host")
+    exe = os.path.join(host, "pt_b200")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", host], check=True, capture_output=True)
+    fixture = os.path.join(root, "tests", "golden", "scenes", "cornell.ptscene")
+    for rng, mode in (("keyed", capi.RNG_KEYED_PHILOX), ("exact", capi.RNG_MT19937_SEQUENTIAL)):
+        out = str(tmp_path / f"cli_{rng}.raw")
+        res = subprocess.run([exe, "--ptscene", fixture, "-w", "48", "-h", "36", "--spp", "3", "--seed", "7",
+                              "--save-every", "0", "--rng", rng, "--raw", out],
+                             capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stderr
+        assert "Scene contains 38 triangles and 1 spheres." in res.stdout
+        assert "Total samples: %d" % (48 * 36 * 3) in res.stdout and "Samples/ms:" in res.stdout
+        sums, counts = ob.read_raw(out)
+        scene = scenes["cornell"]
+        want, _ = capi.render(scene, scene.camera(48, 36), capi.make_params(48, 36, spp=3, seed=7),
+                              capi.make_options(rng_mode=mode))
+        assert np.array_equal(sums, want["sum"]) and (counts == 3).all()

@@ -32,3 +32,39 @@ def test_cli_rejects_bad_arguments():
     res = subprocess.run([exe, "--scene", "nonesuch", "--scenes", "/nonexistent", "out.png"],
                          capture_output=True, text=True)
     assert res.returncode == 1 and "Unknown scene" in res.stderr
+
+
+def test_raw_to_png_merges_like_the_reference_tool(tmp_path):
+    """raw_to_png_b200 out.png a.raw b.raw: sizes and sample totals are reported, the sum is
+    saved as a valid PNG; the reference's own raw file (tests/golden) is accepted as input."""
+    import struct
+    import zlib
+    import numpy as np
+    exe = os.path.join(HOST, "raw_to_png_b200")
+    subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
+    golden = os.path.join(ROOT, "tests", "golden", "render_asis_cornell.raw")
+    out = str(tmp_path / "merged.png")
+    res = subprocess.run([exe, out, golden, golden], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    assert "width: 16 height: 16" in res.stdout and "samples: 3840" in res.stdout
+    assert "with 7680 samples (30.0 per pixel)" in res.stdout
+    data = open(out, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    w, h = struct.unpack(">II", data[16:24])
+    assert (w, h) == (16, 16)
+    # decode the single IDAT chunk and compare with ArrayOutput::pixelAt's formula
+    pos, idat = 8, b""
+    while pos < len(data):
+        n, kind = struct.unpack(">I4s", data[pos:pos + 8])
+        if kind == b"IDAT":
+            idat += data[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), dtype=np.uint8).reshape(16, 1 + 16 * 3)
+    assert (rows[:, 0] == 0).all()
+    from oracle import oracle_binding as ob
+    sums, counts = ob.read_raw(golden)
+    mean = sums / counts[..., None]  # doubling sums and counts leaves the mean unchanged
+    want = np.round(np.clip(mean, 0, 1) ** (1 / 2.2) * 255).astype(np.uint8)
+    assert np.abs(rows[:, 1:].reshape(16, 16, 3).astype(int) - want.astype(int)).max() <= 1
+    res = subprocess.run([exe, out], capture_output=True, text=True)
+    assert res.returncode == 1 and "Missing inputs" in res.stderr
