@@ -910,7 +910,6 @@ __global__ void fp64PeakKernel(double *sink, int iterations) {
 // Host-side launchers (called from ptb200_shim.cu).
 // =============================================================================================
 constexpr int kSequentialWarps = 2;
-constexpr int kDefaultKeyedConfig = 1;
 
 template <int kBlock, int kMinBlocks, int kSweep>
 cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t stream) {
@@ -935,35 +934,38 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
   return cudaGetLastError();
 }
 
-// PTB200_KEYED_CONFIG = 10 * launchShape + sweepVariant selects the megakernel instantiation
-// (tools/sweep_configs.py).  Sweep variants: 0 one-stage FP64, 1 two-stage FP64 (prefilter +
-// exact), 2 FP32 stage 0 + exact, 3 the same with the packed FP32x2 datapath (FFMA2).  Launch shapes: 0 = 256 threads x 2 CTAs/SM (128 registers),
-// 1 = 384 x 1 (168 registers), 2 = 256 x 3 (80 registers).
-static int keyedConfig() {
-  static const int config = [] {
+// A megakernel configuration is 10 * launchShape + sweepVariant.
+//   sweep variants: 0 one-stage FP64; 1 two-stage FP64 (prefilter + exact); 2 FP32 stage 0 + exact;
+//                   3 the same with the packed FP32x2 datapath (FFMA2)
+//   launch shapes:  0 = 256 threads x 2 CTAs/SM (128 registers); 1 = 384 x 1 (168 registers);
+//                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5
+// Default (measured on B200, profiles/): packed FP32 stage 0 everywhere it is usable; three CTAs
+// per SM for small scenes, where shading latency rather than the sweep limits the kernel.
+// PTB200_KEYED_CONFIG overrides it (tools/sweep_configs.py).
+int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
+  static const int forced = [] {
     const char *env = getenv("PTB200_KEYED_CONFIG");
-    return env ? atoi(env) : kDefaultKeyedConfig;
+    return env ? atoi(env) : -1;
   }();
-  return config;
+  if (forced >= 0)
+    return forced;
+  const int sweep = filterUsable ? 3 : 1;
+  const int shape = numTriangles <= 512 ? 2 : 0;
+  return 10 * shape + sweep;
 }
-int keyedSweepVariant() { return keyedConfig() % 10; }
 
-cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, cudaStream_t stream) {
-  switch (keyedConfig()) {
+cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream) {
+  switch (config) {
   case 0: return launchKeyedConfig<256, 2, 0>(args, numSms, stream);
   case 1: return launchKeyedConfig<256, 2, 1>(args, numSms, stream);
   case 2: return launchKeyedConfig<256, 2, 2>(args, numSms, stream);
   case 3: return launchKeyedConfig<256, 2, 3>(args, numSms, stream);
-  case 13: return launchKeyedConfig<384, 1, 3>(args, numSms, stream);
-  case 23: return launchKeyedConfig<256, 3, 3>(args, numSms, stream);
   case 11: return launchKeyedConfig<384, 1, 1>(args, numSms, stream);
-  case 12: return launchKeyedConfig<384, 1, 2>(args, numSms, stream);
+  case 13: return launchKeyedConfig<384, 1, 3>(args, numSms, stream);
   case 21: return launchKeyedConfig<256, 3, 1>(args, numSms, stream);
-  case 31: return launchKeyedConfig<192, 4, 1>(args, numSms, stream);
+  case 23: return launchKeyedConfig<256, 3, 3>(args, numSms, stream);
   case 33: return launchKeyedConfig<192, 4, 3>(args, numSms, stream);
-  case 41: return launchKeyedConfig<128, 5, 1>(args, numSms, stream);
   case 43: return launchKeyedConfig<128, 5, 3>(args, numSms, stream);
-  case 22: return launchKeyedConfig<256, 3, 2>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
 }

@@ -85,10 +85,10 @@ struct IntersectArgs {
 
 size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
                       uint32_t threadsForPrimarySlots);
-int keyedSweepVariant();  // what PTB200_KEYED_CONFIG selects for the megakernel
+int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable); // 10 * launchShape + sweepVariant
 cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream);
 cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream);
-cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, cudaStream_t stream);
+cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream);
 cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream);
 cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream);
 cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream);

@@ -407,7 +407,8 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
     passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(opt.passesPerBatch));
   passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses));
   PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
-  if (!sequential && keyedSweepVariant() >= 2) {
+  const int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable);
+  if (!sequential && keyedConfig % 10 >= 2) {
     if (!ctx->filterUsable)
       return fail(PTB200_EINVAL, "scene coordinates exceed the range the FP32 stage-0 sweep supports; "
                                  "select a FP64 sweep (PTB200_KEYED_CONFIG=1)");
@@ -466,7 +467,7 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.samples = ctx->samples.ptr;
       a.ticket = ctx->counters.ptr;
       a.castCounter = ctx->counters.ptr + 1;
-      PT_CUDA(launchRenderKeyed(a, ctx->numSms, ctx->stream));
+      PT_CUDA(launchRenderKeyed(a, ctx->numSms, keyedConfig, ctx->stream));
     }
     if (events) {
       PT_CUDA(cudaEventRecord(e1, ctx->stream));

@@ -243,7 +243,7 @@ def test_one_stage_sweep_config_renders_identically(scenes, tmp_path):
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
                 root, os.path.join(root, "tests/golden/scenes/suzanne.ptscene"))
     outs = []
-    for config in ("1", "0", "2", "3", "11", "23"):
+    for config in ("1", "0", "2", "3", "13", "23", "43"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
