@@ -25,7 +25,7 @@ struct DeviceScene {
   const double4 *spheres;     // [numSpheres] {centre xyz, radius^2}   (Sphere.h:7-12)
   const uint32_t *sphereMaterial;
   const double *materials;    // [numMaterials][10] MaterialSpec order + 1/indexOfRefraction
-  const float *triFilter;     // [numTiles][13][tileTris] fp32 stage-0 data (see buildFilterKernel)
+  const float *triFilter;     // [numTiles][tileTris/4][14][4] fp32 stage-0 data (buildFilterKernel)
   uint32_t numTriangles;
   uint32_t numSpheres;
   uint32_t tileTris;          // triangles per tile (multiple of 4)
@@ -208,7 +208,8 @@ __device__ __forceinline__ void sweepTilePrefiltered(const double *__restrict__ 
 //   64 FP32 roundoffs, about 4x what a forward error analysis of the 24 operations needs).
 // With s = sign(det32), certain rejection needs |det32| > Ed (the sign is then the reference's)
 // and one of   s*X32 < -2Ex   (=> u < 0),   s*Y32 < -2Ey   (=> v < 0),
-//              s*(X32+Y32) > |det32|*(1+2^-20) + Ed + Ex + Ey   (=> u + v > 1).
+//              s*(X32+Y32) > |det32|*(1+2^-20) + Ed + Ex + Ey   (=> u + v > 1),
+//              s*T32 < -2Et   (=> t = T/det < 0, so `t > Epsilon` fails; T = e2.qVec).
 // NaNs keep the triangle.  Survivors are re-tested with the exact reference arithmetic
 // (testTriangle on the FP64 data in global memory/L1) in index order, so results are bit-identical
 // to the one-stage sweep; the FP64 pipe only sees a handful of triangles per ray.
@@ -217,7 +218,7 @@ struct Stage0Ray {
 };
 __device__ __forceinline__ bool stage0Keep(float v0x, float v0y, float v0z, float e1x, float e1y,
                                            float e1z, float e2x, float e2y, float e2z, float ed,
-                                           float kx, float ky, float k3, const Stage0Ray &r) {
+                                           float kx, float ky, float k3, float kt, const Stage0Ray &r) {
   const float px = fmaf(r.dy, e2z, -(r.dz * e2y));
   const float py = fmaf(r.dz, e2x, -(r.dx * e2z));
   const float pz = fmaf(r.dx, e2y, -(r.dy * e2x));
@@ -228,11 +229,13 @@ __device__ __forceinline__ bool stage0Keep(float v0x, float v0y, float v0z, floa
   const float qy = fmaf(tz, e1x, -(tx * e1z));
   const float qz = fmaf(tx, e1y, -(ty * e1x));
   const float y = fmaf(r.dz, qz, fmaf(r.dy, qy, r.dx * qx));
+  const float t = fmaf(e2z, qz, fmaf(e2y, qy, e2x * qx));
   const uint32_t sign = __float_as_uint(det) & 0x80000000u;
   const float xs = __uint_as_float(__float_as_uint(x) ^ sign);
   const float ys = __uint_as_float(__float_as_uint(y) ^ sign);
+  const float ts = __uint_as_float(__float_as_uint(t) ^ sign);
   const float adet = fabsf(det);
-  const bool certain = (xs < -kx) | (ys < -ky) | (xs + ys > fmaf(adet, 1.0f + 0x1p-20f, k3));
+  const bool certain = (xs < -kx) | (ys < -ky) | (ts < -kt) | (xs + ys > fmaf(adet, 1.0f + 0x1p-20f, k3));
   return (adet <= ed) | !certain;
 }
 
@@ -245,7 +248,7 @@ __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y
 __device__ __forceinline__ unsigned stage0Keep2(float2 v0x, float2 v0y, float2 v0z, float2 e1x,
                                                 float2 e1y, float2 e1z, float2 e2x, float2 e2y,
                                                 float2 e2z, float2 ed, float2 kx, float2 ky,
-                                                float2 k3, const Stage0Ray2 &r) {
+                                                float2 k3, float2 kt, const Stage0Ray2 &r) {
   const float2 px = __ffma2_rn(r.dy, e2z, neg2(__fmul2_rn(r.dz, e2y)));
   const float2 py = __ffma2_rn(r.dz, e2x, neg2(__fmul2_rn(r.dx, e2z)));
   const float2 pz = __ffma2_rn(r.dx, e2y, neg2(__fmul2_rn(r.dy, e2x)));
@@ -257,21 +260,26 @@ __device__ __forceinline__ unsigned stage0Keep2(float2 v0x, float2 v0y, float2 v
   const float2 qy = __ffma2_rn(tz, e1x, neg2(__fmul2_rn(tx, e1z)));
   const float2 qz = __ffma2_rn(tx, e1y, neg2(__fmul2_rn(ty, e1x)));
   const float2 y = __ffma2_rn(r.dz, qz, __ffma2_rn(r.dy, qy, __fmul2_rn(r.dx, qx)));
+  const float2 t = __ffma2_rn(e2z, qz, __ffma2_rn(e2y, qy, __fmul2_rn(e2x, qx)));
   const uint32_t signA = __float_as_uint(det.x) & 0x80000000u, signB = __float_as_uint(det.y) & 0x80000000u;
   const float2 xs = make_float2(__uint_as_float(__float_as_uint(x.x) ^ signA), __uint_as_float(__float_as_uint(x.y) ^ signB));
   const float2 ys = make_float2(__uint_as_float(__float_as_uint(y.x) ^ signA), __uint_as_float(__float_as_uint(y.y) ^ signB));
   const float2 adet = make_float2(fabsf(det.x), fabsf(det.y));
   const float2 sum = __fadd2_rn(xs, ys);
   const float2 bound = __ffma2_rn(adet, make_float2(1.0f + 0x1p-20f, 1.0f + 0x1p-20f), k3);
-  const bool certainA = (xs.x < -kx.x) | (ys.x < -ky.x) | (sum.x > bound.x);
-  const bool certainB = (xs.y < -kx.y) | (ys.y < -ky.y) | (sum.y > bound.y);
+  const float tsA = __uint_as_float(__float_as_uint(t.x) ^ signA), tsB = __uint_as_float(__float_as_uint(t.y) ^ signB);
+  const bool certainA = (xs.x < -kx.x) | (ys.x < -ky.x) | (tsA < -kt.x) | (sum.x > bound.x);
+  const bool certainB = (xs.y < -kx.y) | (ys.y < -ky.y) | (tsB < -kt.y) | (sum.y > bound.y);
   const bool keepA = (adet.x <= ed.x) | !certainA;
   const bool keepB = (adet.y <= ed.y) | !certainB;
   return (keepA ? 1u : 0u) | (keepB ? 2u : 0u);
 }
 
-// `filter` is the FP32 tile in shared memory ([13][tileTris]); `exact` the same tile's FP64
-// sweep data in global memory ([9][tileTris]).  count is a multiple of 4.
+// `filter` is the FP32 tile in shared memory, blocked by groups of four triangles:
+// [group][14][4] floats (v0 xyz, e1 xyz, e2 xyz, Ed, 2Ex, 2Ey, K3, 2Et), so one base register and
+// immediate offsets address all fourteen 16-byte loads; `exact` is the same tile's FP64 sweep
+// data in global memory ([9][tileTris]).  count is a multiple of 4.
+constexpr int kFilterFloats = 14;
 template <bool kPacked>
 __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter,
                                                 const double *__restrict__ exact, int tileTris,
@@ -287,26 +295,27 @@ __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter
     unsigned long long survivors = 0;
 #pragma unroll 1
     for (int i = chunk; i < chunkEnd; i += 4) {
-      float4 a[13];
+      float4 a[kFilterFloats];
+      const float4 *group = reinterpret_cast<const float4 *>(filter) + (i >> 2) * kFilterFloats;
 #pragma unroll
-      for (int k = 0; k < 13; ++k)
-        a[k] = *reinterpret_cast<const float4 *>(filter + k * tileTris + i);
+      for (int k = 0; k < kFilterFloats; ++k)
+        a[k] = group[k];
       unsigned keep;
       if (kPacked) {
 #define PT_LO(k) make_float2(a[k].x, a[k].y)
 #define PT_HI(k) make_float2(a[k].z, a[k].w)
         keep = stage0Keep2(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6), PT_LO(7),
-                           PT_LO(8), PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), r2) |
+                           PT_LO(8), PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), PT_LO(13), r2) |
                (stage0Keep2(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6), PT_HI(7),
-                            PT_HI(8), PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), r2) << 2);
+                            PT_HI(8), PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), PT_HI(13), r2) << 2);
 #undef PT_LO
 #undef PT_HI
       } else
       keep =
-          (stage0Keep(a[0].x, a[1].x, a[2].x, a[3].x, a[4].x, a[5].x, a[6].x, a[7].x, a[8].x, a[9].x, a[10].x, a[11].x, a[12].x, r) ? 1u : 0u) |
-          (stage0Keep(a[0].y, a[1].y, a[2].y, a[3].y, a[4].y, a[5].y, a[6].y, a[7].y, a[8].y, a[9].y, a[10].y, a[11].y, a[12].y, r) ? 2u : 0u) |
-          (stage0Keep(a[0].z, a[1].z, a[2].z, a[3].z, a[4].z, a[5].z, a[6].z, a[7].z, a[8].z, a[9].z, a[10].z, a[11].z, a[12].z, r) ? 4u : 0u) |
-          (stage0Keep(a[0].w, a[1].w, a[2].w, a[3].w, a[4].w, a[5].w, a[6].w, a[7].w, a[8].w, a[9].w, a[10].w, a[11].w, a[12].w, r) ? 8u : 0u);
+          (stage0Keep(a[0].x, a[1].x, a[2].x, a[3].x, a[4].x, a[5].x, a[6].x, a[7].x, a[8].x, a[9].x, a[10].x, a[11].x, a[12].x, a[13].x, r) ? 1u : 0u) |
+          (stage0Keep(a[0].y, a[1].y, a[2].y, a[3].y, a[4].y, a[5].y, a[6].y, a[7].y, a[8].y, a[9].y, a[10].y, a[11].y, a[12].y, a[13].y, r) ? 2u : 0u) |
+          (stage0Keep(a[0].z, a[1].z, a[2].z, a[3].z, a[4].z, a[5].z, a[6].z, a[7].z, a[8].z, a[9].z, a[10].z, a[11].z, a[12].z, a[13].z, r) ? 4u : 0u) |
+          (stage0Keep(a[0].w, a[1].w, a[2].w, a[3].w, a[4].w, a[5].w, a[6].w, a[7].w, a[8].w, a[9].w, a[10].w, a[11].w, a[12].w, a[13].w, r) ? 8u : 0u);
       survivors |= static_cast<unsigned long long>(keep) << (i - chunk);
     }
     while (survivors) { // ascending index: the serial loop's tie-break order

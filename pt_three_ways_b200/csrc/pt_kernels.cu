@@ -31,7 +31,7 @@ __host__ __device__ inline uint32_t smemTileOffset(uint32_t numSpheres) {
 }
 
 constexpr uint32_t kExactBytesPerTriangle = 72;  // 9 doubles
-constexpr uint32_t kFilterBytesPerTriangle = 52; // 13 floats
+constexpr uint32_t kFilterBytesPerTriangle = 56; // 14 floats
 __host__ __device__ inline uint32_t sweepBytesPerTriangle(int sweep) {
   return sweep >= 2 ? kFilterBytesPerTriangle : kExactBytesPerTriangle;
 }
@@ -817,40 +817,46 @@ __global__ void buildFilterKernel(const __grid_constant__ BuildFilterArgs args) 
     return;
   const uint32_t tile = slot / scene.tileTris, within = slot % scene.tileTris;
   const double *src = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris + within;
-  float *dst = args.out + static_cast<size_t>(tile) * 13 * scene.tileTris + within;
+  // blocked layout: [tile][group of 4][14][4]
+  float *dst = args.out + (static_cast<size_t>(tile) * (scene.tileTris / 4) + within / 4) * (kFilterFloats * 4) +
+               within % 4;
   double v[9];
   for (int k = 0; k < 9; ++k) {
     v[k] = src[static_cast<size_t>(k) * scene.tileTris];
-    dst[static_cast<size_t>(k) * scene.tileTris] = __double2float_rn(v[k]);
+    dst[k * 4] = __double2float_rn(v[k]);
   }
   const bool padding = slot >= scene.numTriangles;
   const double lenV0 = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
   const double lenE1 = sqrt(v[3] * v[3] + v[4] * v[4] + v[5] * v[5]);
   const double lenE2 = sqrt(v[6] * v[6] + v[7] * v[7] + v[8] * v[8]);
-  // 2^-18 = 64 FP32 unit roundoffs (2^-24): |det32 - det| <= ~13u |e1||e2|,
-  // |X32 - X| <= ~16u (|o|+|v0|)|e2|, |Y32 - Y| <= ~18u (|o|+|v0|)|e1| by forward error analysis
-  // of the 24 operations on inputs rounded to FP32; the rest is safety margin, which also
-  // covers the rounding of the comparisons themselves.
+  // 2^-18 = 64 FP32 unit roundoffs (2^-24).  Forward error analysis of the 24 (+3) operations
+  // on inputs rounded to FP32 gives |det32 - det| <= ~13u |e1||e2|, |X32 - X| <= ~16u r|e2|,
+  // |Y32 - Y| <= ~18u r|e1|, |T32 - T| <= ~18u r|e1||e2| with r = |o| + |v0|; the rest is safety
+  // margin, which also covers the rounding of the comparisons themselves.
   const double c = 0x1p-18;
   const double reach = args.originBound + lenV0;
   const double ed = c * lenE1 * lenE2;
   const double ex = c * lenE2 * reach;
   const double ey = c * lenE1 * reach;
+  const double et = c * lenE1 * lenE2 * reach;
   const double slack = 1.0 + 0x1p-10;
   float fed = __double2float_ru(ed * slack);
   float fkx = __double2float_ru(2.0 * ex * slack);
   float fky = __double2float_ru(2.0 * ey * slack);
   float fk3 = __double2float_ru((ed * (1.0 + 0x1p-20) + ex + ey) * slack);
+  float fkt = __double2float_ru(2.0 * et * slack);
   if (padding) { // all-zero padding triangles: make stage 0 reject them outright
     fed = -1.0f;
     fkx = -1.0f;
     fky = -1.0f;
     fk3 = 0.0f;
+    fkt = 0.0f;
   }
-  dst[static_cast<size_t>(9) * scene.tileTris] = fed;
-  dst[static_cast<size_t>(10) * scene.tileTris] = fkx;
-  dst[static_cast<size_t>(11) * scene.tileTris] = fky;
-  dst[static_cast<size_t>(12) * scene.tileTris] = fk3;
+  dst[9 * 4] = fed;
+  dst[10 * 4] = fkx;
+  dst[11 * 4] = fky;
+  dst[12 * 4] = fk3;
+  dst[13 * 4] = fkt;
 }
 
 // For every (ray, triangle): does stage 0 keep it, does the exact test accept it (with no
@@ -866,11 +872,12 @@ __global__ void auditStage0Kernel(const __grid_constant__ AuditArgs args) {
                       static_cast<float>(d.x), static_cast<float>(d.y), static_cast<float>(d.z)};
     for (uint32_t index = 0; index < scene.numTriangles; ++index) {
       const uint32_t tile = index / scene.tileTris, i = index % scene.tileTris;
-      const float *f = scene.triFilter + static_cast<size_t>(tile) * 13 * scene.tileTris + i;
+      const float *f = scene.triFilter +
+                       (static_cast<size_t>(tile) * (scene.tileTris / 4) + i / 4) * (kFilterFloats * 4) + i % 4;
       const double *e = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris + i;
       const uint32_t n = scene.tileTris;
-      const bool keep = stage0Keep(f[0], f[n], f[2 * n], f[3 * n], f[4 * n], f[5 * n], f[6 * n], f[7 * n],
-                                   f[8 * n], f[9 * n], f[10 * n], f[11 * n], f[12 * n], r);
+      const bool keep = stage0Keep(f[0], f[4], f[8], f[12], f[16], f[20], f[24], f[28], f[32], f[36], f[40], f[44],
+                                   f[48], f[52], r);
       Nearest best{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim};
       testTriangle(mk(e[0], e[n], e[2 * n]), mk(e[3 * n], e[4 * n], e[5 * n]), mk(e[6 * n], e[7 * n], e[8 * n]),
                    o, d, static_cast<int>(index), best);

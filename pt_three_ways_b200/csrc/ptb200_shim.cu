@@ -337,7 +337,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
 
   PT_CUDA(ctx->triSweep.ensure(sweepDoubles));
   PT_CUDA(ctx->triShade.ensure(shade.size()));
-  PT_CUDA(ctx->triFilter.ensure(static_cast<size_t>(d.numTiles) * 13 * d.tileTris));
+  PT_CUDA(ctx->triFilter.ensure(static_cast<size_t>(d.numTiles) * 14 * d.tileTris));
   PT_CUDA(ctx->spheres.ensure(spheres.size()));
   PT_CUDA(ctx->sphereMaterial.ensure(scene->numSpheres));
   PT_CUDA(ctx->materials.ensure(static_cast<size_t>(scene->numMaterials) * 10));
