@@ -184,7 +184,7 @@ def render(scene, camera18, params: PtRenderParams, options: PtRenderOptions | N
     return out, _stats_dict(st)
 
 
-SWEEP_ONE_STAGE, SWEEP_TWO_STAGE_FP64, SWEEP_FP32_STAGE0, SWEEP_FP32X2_STAGE0 = 0, 1, 2, 3
+SWEEP_ONE_STAGE, SWEEP_TWO_STAGE_FP64, SWEEP_FP32_STAGE0, SWEEP_FP32X2_STAGE0, SWEEP_FP32X2_STAGE0_T = 0, 1, 2, 3, 4
 
 
 def intersect(scene, rays, which=0, nearer_than=float("inf"), device=0, warp_cooperative=False,

@@ -245,6 +245,7 @@ struct Stage0Ray2 {
   float2 ox, oy, oz, dx, dy, dz; // each component duplicated into both halves
 };
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+template <bool kRejectNegativeT>
 __device__ __forceinline__ unsigned stage0Keep2(float2 v0x, float2 v0y, float2 v0z, float2 e1x,
                                                 float2 e1y, float2 e1z, float2 e2x, float2 e2y,
                                                 float2 e2z, float2 ed, float2 kx, float2 ky,
@@ -260,16 +261,19 @@ __device__ __forceinline__ unsigned stage0Keep2(float2 v0x, float2 v0y, float2 v
   const float2 qy = __ffma2_rn(tz, e1x, neg2(__fmul2_rn(tx, e1z)));
   const float2 qz = __ffma2_rn(tx, e1y, neg2(__fmul2_rn(ty, e1x)));
   const float2 y = __ffma2_rn(r.dz, qz, __ffma2_rn(r.dy, qy, __fmul2_rn(r.dx, qx)));
-  const float2 t = __ffma2_rn(e2z, qz, __ffma2_rn(e2y, qy, __fmul2_rn(e2x, qx)));
   const uint32_t signA = __float_as_uint(det.x) & 0x80000000u, signB = __float_as_uint(det.y) & 0x80000000u;
   const float2 xs = make_float2(__uint_as_float(__float_as_uint(x.x) ^ signA), __uint_as_float(__float_as_uint(x.y) ^ signB));
   const float2 ys = make_float2(__uint_as_float(__float_as_uint(y.x) ^ signA), __uint_as_float(__float_as_uint(y.y) ^ signB));
   const float2 adet = make_float2(fabsf(det.x), fabsf(det.y));
   const float2 sum = __fadd2_rn(xs, ys);
   const float2 bound = __ffma2_rn(adet, make_float2(1.0f + 0x1p-20f, 1.0f + 0x1p-20f), k3);
-  const float tsA = __uint_as_float(__float_as_uint(t.x) ^ signA), tsB = __uint_as_float(__float_as_uint(t.y) ^ signB);
-  const bool certainA = (xs.x < -kx.x) | (ys.x < -ky.x) | (tsA < -kt.x) | (sum.x > bound.x);
-  const bool certainB = (xs.y < -kx.y) | (ys.y < -ky.y) | (tsB < -kt.y) | (sum.y > bound.y);
+  bool certainA = (xs.x < -kx.x) | (ys.x < -ky.x) | (sum.x > bound.x);
+  bool certainB = (xs.y < -kx.y) | (ys.y < -ky.y) | (sum.y > bound.y);
+  if (kRejectNegativeT) { // worth its 3 packed operations only when survivors dominate (small scenes)
+    const float2 t = __ffma2_rn(e2z, qz, __ffma2_rn(e2y, qy, __fmul2_rn(e2x, qx)));
+    certainA |= __uint_as_float(__float_as_uint(t.x) ^ signA) < -kt.x;
+    certainB |= __uint_as_float(__float_as_uint(t.y) ^ signB) < -kt.y;
+  }
   const bool keepA = (adet.x <= ed.x) | !certainA;
   const bool keepB = (adet.y <= ed.y) | !certainB;
   return (keepA ? 1u : 0u) | (keepB ? 2u : 0u);
@@ -280,7 +284,7 @@ __device__ __forceinline__ unsigned stage0Keep2(float2 v0x, float2 v0y, float2 v
 // immediate offsets address all fourteen 16-byte loads; `exact` is the same tile's FP64 sweep
 // data in global memory ([9][tileTris]).  count is a multiple of 4.
 constexpr int kFilterFloats = 14;
-template <bool kPacked>
+template <bool kPacked, bool kRejectNegativeT>
 __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter,
                                                 const double *__restrict__ exact, int tileTris,
                                                 int count, int firstIndex, V3 o, V3 d,
@@ -304,9 +308,9 @@ __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter
       if (kPacked) {
 #define PT_LO(k) make_float2(a[k].x, a[k].y)
 #define PT_HI(k) make_float2(a[k].z, a[k].w)
-        keep = stage0Keep2(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6), PT_LO(7),
+        keep = stage0Keep2<kRejectNegativeT>(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6), PT_LO(7),
                            PT_LO(8), PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), PT_LO(13), r2) |
-               (stage0Keep2(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6), PT_HI(7),
+               (stage0Keep2<kRejectNegativeT>(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6), PT_HI(7),
                             PT_HI(8), PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), PT_HI(13), r2) << 2);
 #undef PT_LO
 #undef PT_HI

@@ -122,7 +122,7 @@ __device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const 
   const int tileTris = static_cast<int>(scene.tileTris);
   const int first = static_cast<int>(tileIndex * scene.tileTris);
   if (kSweep >= 2)
-    sweepTileStage0<kSweep == 3>(reinterpret_cast<const float *>(tile),
+    sweepTileStage0<kSweep >= 3, kSweep == 4>(reinterpret_cast<const float *>(tile),
                     scene.triSweep + static_cast<size_t>(tileIndex) * 9 * scene.tileTris, tileTris, tileTris,
                     first, o, d, best);
   else if (kSweep == 1)
@@ -772,7 +772,9 @@ __global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
     if (args.which != 1) {
       for (uint32_t j = 0; j < scene.numTiles; ++j) {
         const unsigned char *tile = stream.acquire();
-        if (args.sweep == 3)
+        if (args.sweep == 4)
+          sweepStagedTile<4>(scene, tile, j, o, d, best);
+        else if (args.sweep == 3)
           sweepStagedTile<3>(scene, tile, j, o, d, best);
         else if (args.sweep == 2)
           sweepStagedTile<2>(scene, tile, j, o, d, best);
@@ -943,7 +945,8 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
 
 // A megakernel configuration is 10 * launchShape + sweepVariant.
 //   sweep variants: 0 one-stage FP64; 1 two-stage FP64 (prefilter + exact); 2 FP32 stage 0 + exact;
-//                   3 the same with the packed FP32x2 datapath (FFMA2)
+//                   3 the same with the packed FP32x2 datapath (FFMA2); 4 = 3 + stage 0 also
+//                   rejects triangles certainly behind the ray (pays off on small scenes)
 //   launch shapes:  0 = 256 threads x 2 CTAs/SM (128 registers); 1 = 384 x 1 (168 registers);
 //                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5
 // Default (measured on B200, profiles/): packed FP32 stage 0 everywhere it is usable; three CTAs
@@ -956,8 +959,9 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
   }();
   if (forced >= 0)
     return forced;
-  const int sweep = filterUsable ? 3 : 1;
-  const int shape = numTriangles <= 512 ? 2 : 0;
+  const bool small = numTriangles <= 512;
+  const int sweep = filterUsable ? (small ? 4 : 3) : 1;
+  const int shape = small ? 2 : 0;
   return 10 * shape + sweep;
 }
 
@@ -971,6 +975,9 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
   case 13: return launchKeyedConfig<384, 1, 3>(args, numSms, stream);
   case 21: return launchKeyedConfig<256, 3, 1>(args, numSms, stream);
   case 23: return launchKeyedConfig<256, 3, 3>(args, numSms, stream);
+  case 4: return launchKeyedConfig<256, 2, 4>(args, numSms, stream);
+  case 24: return launchKeyedConfig<256, 3, 4>(args, numSms, stream);
+  case 34: return launchKeyedConfig<192, 4, 4>(args, numSms, stream);
   case 33: return launchKeyedConfig<192, 4, 3>(args, numSms, stream);
   case 43: return launchKeyedConfig<128, 5, 3>(args, numSms, stream);
   default: return cudaErrorInvalidValue;

@@ -75,7 +75,7 @@ __device__ __forceinline__ double kernelCos(double r) {
   p = fma(p, z, 4.16666666666666019037e-02);
   return fma(z * z, p, fma(-0.5, z, 1.0));
 }
-__device__ __forceinline__ void sinCos(double x, double &s, double &c) {
+static __device__ __noinline__ void sinCos(double x, double &s, double &c) {
   const double kd = rint(x * 6.36619772367581382433e-01); // round half to even
   const int k = static_cast<int>(kd);
   double r = fma(-kd, 1.57079632673412561417e+00, x);
@@ -128,8 +128,8 @@ struct Philox4 {
 };
 constexpr uint32_t kPhiloxKeyHigh = 0xB200D0D0u;
 // Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0,k1).
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
-                                                 uint32_t c3, uint32_t k0, uint32_t k1) {
+static __device__ __noinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                      uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int round = 0; round < 10; ++round) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;

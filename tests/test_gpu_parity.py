@@ -53,7 +53,7 @@ def assert_hits_equal(got, want):
 
 
 @pytest.mark.parametrize("name", SCENE_NAMES)
-@pytest.mark.parametrize("sweep", ["two-stage", "one-stage", "fp32-stage0", "fp32x2-stage0", "warp-cooperative"])
+@pytest.mark.parametrize("sweep", ["two-stage", "one-stage", "fp32-stage0", "fp32x2-stage0", "fp32x2-stage0-t", "warp-cooperative"])
 def test_intersect_matches_oracle(name, sweep, scenes, oracle, capi):
     """Every sweep implementation (two-stage FP64 prefilter + exact, plain one-stage, FP32 stage 0 +
     exact, the sequential kernel's lane-strided sweep) returns the oracle's nearest hit bit for bit."""
@@ -61,7 +61,8 @@ def test_intersect_matches_oracle(name, sweep, scenes, oracle, capi):
     rays = random_rays(scene, 3000 if name != "ce" else 1500, seed=sum(map(ord, name)))
     want = oracle.OracleScene(scene).intersect(rays)
     variant = {"two-stage": capi.SWEEP_TWO_STAGE_FP64, "one-stage": capi.SWEEP_ONE_STAGE,
-               "fp32-stage0": capi.SWEEP_FP32_STAGE0, "fp32x2-stage0": capi.SWEEP_FP32X2_STAGE0}.get(sweep)
+               "fp32-stage0": capi.SWEEP_FP32_STAGE0, "fp32x2-stage0": capi.SWEEP_FP32X2_STAGE0,
+               "fp32x2-stage0-t": capi.SWEEP_FP32X2_STAGE0_T}.get(sweep)
     got = capi.intersect(scene, rays, warp_cooperative=sweep == "warp-cooperative", sweep=variant)
     assert (want[:, 0] != 0).sum() > 100
     assert_hits_equal(got, want)
@@ -243,7 +244,7 @@ def test_one_stage_sweep_config_renders_identically(scenes, tmp_path):
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
                 root, os.path.join(root, "tests/golden/scenes/suzanne.ptscene"))
     outs = []
-    for config in ("1", "0", "2", "3", "13", "23", "43"):
+    for config in ("1", "0", "2", "3", "4", "13", "24", "43"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
