@@ -26,6 +26,8 @@ struct DeviceScene {
   const uint32_t *sphereMaterial;
   const double *materials;    // [numMaterials][10] MaterialSpec order + 1/indexOfRefraction
   const float *triFilter;     // [numTiles][tileTris/4][14][4] fp32 stage-0 data (buildFilterKernel)
+  const double *triExact;     // [numTiles*tileTris][10] AoS copy of the 9 sweep doubles (+pad) for the
+                              //   survivors' exact test: one address, five 16-byte loads
   uint32_t numTriangles;
   uint32_t numSpheres;
   uint32_t tileTris;          // triangles per tile (multiple of 4)
@@ -281,8 +283,8 @@ __device__ __forceinline__ unsigned stage0Keep2(float2 v0x, float2 v0y, float2 v
 
 // `filter` is the FP32 tile in shared memory, blocked by groups of four triangles:
 // [group][14][4] floats (v0 xyz, e1 xyz, e2 xyz, Ed, 2Ex, 2Ey, K3, 2Et), so one base register and
-// immediate offsets address all fourteen 16-byte loads; `exact` is the same tile's FP64 sweep
-// data in global memory ([9][tileTris]).  count is a multiple of 4.
+// immediate offsets address all fourteen 16-byte loads; `exact` is the tile's first record in the
+// AoS FP64 array (10 doubles per triangle, global memory / L1).  count is a multiple of 4.
 constexpr int kFilterFloats = 14;
 template <bool kPacked, bool kRejectNegativeT>
 __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter,
@@ -325,10 +327,10 @@ __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter
     while (survivors) { // ascending index: the serial loop's tie-break order
       const int i = chunk + __ffsll(static_cast<long long>(survivors)) - 1;
       survivors &= survivors - 1;
-      testTriangle(mk(__ldg(exact + 0 * tileTris + i), __ldg(exact + 1 * tileTris + i), __ldg(exact + 2 * tileTris + i)),
-                   mk(__ldg(exact + 3 * tileTris + i), __ldg(exact + 4 * tileTris + i), __ldg(exact + 5 * tileTris + i)),
-                   mk(__ldg(exact + 6 * tileTris + i), __ldg(exact + 7 * tileTris + i), __ldg(exact + 8 * tileTris + i)),
-                   o, d, firstIndex + i, best);
+      const double2 *record = reinterpret_cast<const double2 *>(exact + 10 * static_cast<size_t>(i));
+      const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
+                    a4 = __ldg(record + 4);
+      testTriangle(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d, firstIndex + i, best);
     }
   }
 }

@@ -123,8 +123,7 @@ __device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const 
   const int first = static_cast<int>(tileIndex * scene.tileTris);
   if (kSweep >= 2)
     sweepTileStage0<kSweep >= 3, kSweep == 4>(reinterpret_cast<const float *>(tile),
-                    scene.triSweep + static_cast<size_t>(tileIndex) * 9 * scene.tileTris, tileTris, tileTris,
-                    first, o, d, best);
+                    scene.triExact + static_cast<size_t>(first) * 10, tileTris, tileTris, first, o, d, best);
   else if (kSweep == 1)
     sweepTilePrefiltered(reinterpret_cast<const double *>(tile), tileTris, tileTris, first, o, d, best);
   else
@@ -181,6 +180,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   const DeviceScene &scene = args.scene;
   TileStream stream = makeTileStream(smemRaw, scene, kSweep);
   stream.start();
+#pragma unroll 1
   for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += kBlock)
     stream.spheres()[i] = scene.spheres[i];
   __syncthreads();
@@ -340,6 +340,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       if (depth == 0) {
         if (terminalPrimary) { // maxDepth == 1: numSub children, each Vec3()
           acc = mk(0, 0, 0);
+#pragma unroll 1
           for (int k = 0; k < numSub; ++k)
             acc = add(acc, incoming);
           colour = scale(acc, invNumSub);
@@ -348,6 +349,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       } else {
         // unwind levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum), then the
         // primary hit's own term, in the reference's summation order
+#pragma unroll 1
         for (int level = depth - 1; level >= 1; --level)
           incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
         acc = add(acc, shadeTerm(materialOf(scene, primaryMaterial), primarySpecular, incoming));
@@ -417,6 +419,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   if (!resident)
     stream.drain();
   // one atomic per warp for the cast counter
+#pragma unroll 1
   for (int offset = 16; offset > 0; offset >>= 1)
     casts += __shfl_down_sync(kFullMask, casts, offset);
   if (lane == 0 && casts)
@@ -529,10 +532,11 @@ __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o,
     // nearerThan() encodes; per lane the strict `<` keeps the lowest index among equals.
     for (uint32_t tile = 0; tile < scene.numTiles; ++tile) {
       const double *base = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris;
+      // Padding triangles are all-zero (det == 0) and reject themselves; two per iteration so
+      // the second test's arithmetic overlaps the first one's latency (one warp per scheduler).
+#pragma unroll 2
       for (uint32_t i = lane; i < scene.tileTris; i += 32) {
         const uint32_t index = tile * scene.tileTris + i;
-        if (index >= scene.numTriangles)
-          break;
         const V3 v0 = mk(__ldg(base + 0 * scene.tileTris + i), __ldg(base + 1 * scene.tileTris + i),
                          __ldg(base + 2 * scene.tileTris + i));
         const V3 e1 = mk(__ldg(base + 3 * scene.tileTris + i), __ldg(base + 4 * scene.tileTris + i),

@@ -116,6 +116,7 @@ struct PtContext {
   DeviceBuffer<uint32_t> sphereMaterial;
   DeviceBuffer<double> materials;
   DeviceBuffer<float> triFilter;
+  DeviceBuffer<double> triExact;
   double sceneRadius{0};       // >= |p| for every vertex / sphere surface point
   double filterOriginBound{-1}; // origin bound the current triFilter contents were built for
   bool filterUsable{false};    // FP32 stage 0 allowed (coordinates comfortably inside FP32 range)
@@ -295,6 +296,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
 
   const size_t sweepDoubles = static_cast<size_t>(d.numTiles) * 9 * d.tileTris;
   std::vector<double> sweep(sweepDoubles, 0.0);
+  std::vector<double> exact(static_cast<size_t>(d.numTiles) * d.tileTris * 10, 0.0);
   std::vector<double4> shade(static_cast<size_t>(scene->numTriangles) * 4);
   for (uint32_t i = 0; i < scene->numTriangles; ++i) {
     const double *t = scene->triangleVertices + 9 * static_cast<size_t>(i);
@@ -303,8 +305,10 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
     const uint32_t tile = i / d.tileTris, within = i % d.tileTris;
     double *base = sweep.data() + static_cast<size_t>(tile) * 9 * d.tileTris + within;
     const double values[9] = {v0.x, v0.y, v0.z, e1.x, e1.y, e1.z, e2.x, e2.y, e2.z};
-    for (int a = 0; a < 9; ++a)
+    for (int a = 0; a < 9; ++a) {
       base[static_cast<size_t>(a) * d.tileTris] = values[a];
+      exact[10 * static_cast<size_t>(i) + a] = values[a];
+    }
     const H3 n = shadingNormal(e1, e2);
     H3 fx, fy, bx, by;
     basisFromZ(n, fx, fy);
@@ -338,6 +342,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   PT_CUDA(ctx->triSweep.ensure(sweepDoubles));
   PT_CUDA(ctx->triShade.ensure(shade.size()));
   PT_CUDA(ctx->triFilter.ensure(static_cast<size_t>(d.numTiles) * 14 * d.tileTris));
+  PT_CUDA(ctx->triExact.ensure(exact.size()));
   PT_CUDA(ctx->spheres.ensure(spheres.size()));
   PT_CUDA(ctx->sphereMaterial.ensure(scene->numSpheres));
   PT_CUDA(ctx->materials.ensure(static_cast<size_t>(scene->numMaterials) * 10));
@@ -346,8 +351,10 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
     std::memcpy(&materials[10 * static_cast<size_t>(i)], &scene->materials[i], 72);
     materials[10 * static_cast<size_t>(i) + 9] = 1.0 / scene->materials[i].indexOfRefraction;
   }
-  if (sweepDoubles)
+  if (sweepDoubles) {
     PT_CUDA(cudaMemcpyAsync(ctx->triSweep.ptr, sweep.data(), sweepDoubles * 8, cudaMemcpyHostToDevice, ctx->stream));
+    PT_CUDA(cudaMemcpyAsync(ctx->triExact.ptr, exact.data(), exact.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  }
   if (!shade.empty())
     PT_CUDA(cudaMemcpyAsync(ctx->triShade.ptr, shade.data(), shade.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
   if (!spheres.empty()) {
@@ -363,6 +370,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   d.sphereMaterial = ctx->sphereMaterial.ptr;
   d.materials = ctx->materials.ptr;
   d.triFilter = ctx->triFilter.ptr;
+  d.triExact = ctx->triExact.ptr;
   d.environment[0] = scene->environment[0];
   d.environment[1] = scene->environment[1];
   d.environment[2] = scene->environment[2];
