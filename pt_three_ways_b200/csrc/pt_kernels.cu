@@ -532,9 +532,9 @@ __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o,
     // nearerThan() encodes; per lane the strict `<` keeps the lowest index among equals.
     for (uint32_t tile = 0; tile < scene.numTiles; ++tile) {
       const double *base = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris;
-      // Padding triangles are all-zero (det == 0) and reject themselves; two per iteration so
-      // the second test's arithmetic overlaps the first one's latency (one warp per scheduler).
-#pragma unroll 2
+      // Padding triangles are all-zero (det == 0) and reject themselves.  (Unrolling this loop
+      // by two was measured: 10 % slower, profiles/seq_r1j.jsonl.)
+#pragma unroll 1
       for (uint32_t i = lane; i < scene.tileTris; i += 32) {
         const uint32_t index = tile * scene.tileTris + i;
         const V3 v0 = mk(__ldg(base + 0 * scene.tileTris + i), __ldg(base + 1 * scene.tileTris + i),

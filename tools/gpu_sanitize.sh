@@ -18,8 +18,9 @@ for name, w, h in (("cornell", 24, 18), ("ce", 8, 6), ("bbc-owl", 16, 12)):
     capi.intersect(scene, rays, warp_cooperative=True)
 PY
 for tool in memcheck racecheck synccheck; do
-  for cfg in "" 1 24 3; do
+  for cfg in auto 1 3 0; do
     echo "== compute-sanitizer --tool $tool PTB200_KEYED_CONFIG=$cfg"
-    PTB200_KEYED_CONFIG=$cfg timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_render.py 2>&1 | tail -4
+    if [ "$cfg" = "auto" ]; then unset PTB200_KEYED_CONFIG; else export PTB200_KEYED_CONFIG=$cfg; fi
+    timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_render.py 2>&1 | tail -4
   done
 done | tee $OUT/sanitizer.log
