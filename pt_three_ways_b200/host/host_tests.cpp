@@ -18,6 +18,7 @@
 #include <cstring>
 #include <fstream>
 #include <iostream>
+#include <limits>
 #include <sstream>
 #include <unistd.h>
 
@@ -210,6 +211,105 @@ static void sceneAdaptorTests() {
   }
 }
 
+// The reference's own dod tests (test/dod/SphereTests.cpp:15-52, SceneTests.cpp:16-79,
+// TriangleTests.cpp:15-42), run through the drop-in ptb200::Scene on the GPU.
+static bool near(double a, double b, double tol = 1e-4) { return std::fabs(a - b) <= tol; }
+static bool nearVec(const Vec3 &v, double x, double y, double z) {
+  return near(v.x(), x) && near(v.y(), y) && near(v.z(), z); // ApproxVec3, 1e-4
+}
+static void gpuReferenceKats() {
+  const double inf = std::numeric_limits<double>::infinity();
+  MaterialSpec mat;
+  {
+    Scene scene;
+    scene.addSphere(Vec3(10, 20, 30), 15, mat);
+    CHECK(!scene.intersectSpheres(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(0, 1, 0)), inf));
+    CHECK(!scene.intersectSpheres(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(-10, -20, -30)), inf));
+    auto ir = scene.intersectSpheres(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(10, 20, 30)), inf);
+    CHECK(ir.has_value());
+    if (ir) {
+      CHECK(near(ir->hit.distance, 22.416738, 1e-5));
+      CHECK(nearVec(ir->hit.position, 5.99108, 11.9822, 17.9732));
+      CHECK(nearVec(ir->hit.normal, -0.267261, -0.534522, -0.801784));
+      CHECK(!ir->hit.inside);
+    }
+    CHECK(!scene.intersectSpheres(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(10, 20, 30)), 22.0));
+    CHECK(!scene.intersect(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(0, 1, 0))));
+  }
+  {
+    Scene scene;
+    scene.addSphere(Vec3(0, 0, 30), 10, mat);
+    auto ir = scene.intersectSpheres(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(0, 0, 2)), inf);
+    CHECK(ir && ir->hit.distance == 20 && !ir->hit.inside);
+    if (ir) {
+      CHECK(nearVec(ir->hit.position, 0, 0, 20));
+      CHECK(nearVec(ir->hit.normal, 0, 0, -1));
+    }
+    ir = scene.intersectSpheres(Ray::fromTwoPoints(Vec3(0, 0, 30), Vec3(0, 0, 2)), inf);
+    CHECK(ir && ir->hit.distance == 10 && ir->hit.inside);
+    if (ir)
+      CHECK(nearVec(ir->hit.normal, 0, 0, 1));
+  }
+  for (int order = 0; order < 2; ++order) { // picks the nearer of two spheres, either insertion order
+    Scene scene;
+    const auto m1 = MaterialSpec::makeDiffuse(Vec3(1, 1, 1)), m2 = MaterialSpec::makeDiffuse(Vec3(1, 0, 0));
+    scene.addSphere(Vec3(0, 0, order ? 90 : 30), 10, m1);
+    scene.addSphere(Vec3(0, 0, order ? 30 : 90), 10, m2);
+    auto ir = scene.intersect(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(0, 0, 2)));
+    CHECK(ir && ir->hit.distance == 20);
+    if (ir)
+      CHECK(ir->material == (order ? m2 : m1));
+  }
+  for (int winding = 0; winding < 2; ++winding) {
+    Scene scene;
+    if (winding == 0)
+      scene.addTriangle(Vec3(0, 0, 3), Vec3(0, 1, 3), Vec3(1, 1, 3), mat);
+    else
+      scene.addTriangle(Vec3(0, 0, 3), Vec3(1, 1, 3), Vec3(0, 1, 3), mat);
+    CHECK(!scene.intersectTriangles(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(0, 1, 0)), inf));
+    CHECK(!scene.intersectTriangles(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(0, 0, -1)), inf));
+    auto ir = scene.intersectTriangles(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(0, 0, 1)), inf);
+    CHECK(ir.has_value());
+    if (ir) {
+      CHECK(near(ir->hit.distance, 3.0, 1e-9));
+      CHECK(nearVec(ir->hit.position, 0, 0, 3));
+      CHECK(nearVec(ir->hit.normal, 0, 0, -1));
+    }
+    if (winding == 0)
+      CHECK(!scene.intersectTriangles(Ray::fromTwoPoints(Vec3(0, 0, 0), Vec3(0, 0, 1)), 2.999));
+  }
+  // render() through the adaptor: sample counts, determinism (test/seed_tests.sh), updateFunc
+  Scene scene;
+  scene.addSphere(Vec3(0, 0, 5), 1, MaterialSpec::makeLight(Vec3(2, 2, 2)));
+  scene.addTriangle(Vec3(-5, -1, 0), Vec3(5, -1, 0), Vec3(0, -1, 10), MaterialSpec::makeDiffuse(Vec3(0.5, 0.5, 0.5)));
+  scene.setEnvironmentColour(Vec3(0.1, 0.1, 0.1));
+  RenderParams p;
+  p.width = 16;
+  p.height = 16;
+  p.samplesPerPixel = 16;
+  p.seed = 1;
+  Camera cam(Vec3(0, 0, 0), Vec3(0, 0, 5), Vec3(0, 1, 0).normalised(), 16, 16, 50.0);
+  int updates = 0;
+  const ArrayOutput a = scene.render(cam, p, [&](ArrayOutput &partial) {
+    ++updates;
+    CHECK(partial.width() == 16 && partial.totalSamples() % 256 == 0);
+  });
+  CHECK(updates >= 1);
+  CHECK(a.totalSamples() == 16u * 16u * 16u);
+  const ArrayOutput b = scene.render(cam, p, nullptr);
+  p.seed = 2;
+  const ArrayOutput c = scene.render(cam, p, nullptr);
+  bool same = true, differs = false;
+  for (int y = 0; y < 16; ++y)
+    for (int x = 0; x < 16; ++x) {
+      same = same && a.rawPixelAt(x, y) == b.rawPixelAt(x, y);
+      differs = differs || a.rawPixelAt(x, y) != c.rawPixelAt(x, y);
+    }
+  CHECK(same);
+  CHECK(differs);
+  CHECK(a.rawPixelAt(8, 8).x() > 1.0); // looks straight at the light
+}
+
 static void pngWriterTests() {
   char path[] = "/tmp/ptb200pngXXXXXX";
   const int fd = mkstemp(path);
@@ -324,9 +424,14 @@ int main(int argc, char **argv) {
   mathTests();
   sceneAdaptorTests();
   pngWriterTests();
+  int32_t deviceCount = 0;
+  ptb200_device_count(&deviceCount);
+  if (deviceCount > 0)
+    gpuReferenceKats();
   const bool haveObj = static_cast<bool>(std::ifstream(scenesDir + "/CornellBox-Original.obj"));
   recipeTests(scenesDir, fixtureDir, haveObj);
   std::cout << checks << " checks, " << failures << " failures"
+            << (deviceCount > 0 ? " (GPU KATs ran)" : " (no GPU: KATs through the adaptor skipped)")
             << (haveObj ? "" : " (OBJ-backed recipes skipped: no scenes dir)") << "\n";
   return failures ? 1 : 0;
 }

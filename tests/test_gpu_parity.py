@@ -279,3 +279,17 @@ def test_cpp_host_adaptor_and_cli_render_identically(scenes, capi, tmp_path):
         want, _ = capi.render(scene, scene.camera(48, 36), capi.make_params(48, 36, spp=3, seed=7),
                               capi.make_options(rng_mode=mode))
         assert np.array_equal(sums, want["sum"]) and (counts == 3).all()
+
+
+def test_reference_dod_tests_through_the_cpp_adaptor():
+    """test/dod/{Sphere,Scene,Triangle}Tests.cpp restated against ptb200::Scene (the drop-in for
+    dod::Scene), executed on the GPU through the C ABI, plus render() semantics."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "pt_three_ways_b200", "host")
+    subprocess.run(["make", "-C", host], check=True, capture_output=True)
+    res = subprocess.run([os.path.join(host, "host_tests"), "--fixtures", os.path.join(root, "tests/golden/scenes")],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert " 0 failures" in res.stdout and "GPU KATs ran" in res.stdout
