@@ -122,7 +122,7 @@ __device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const 
   const int tileTris = static_cast<int>(scene.tileTris);
   const int first = static_cast<int>(tileIndex * scene.tileTris);
   if (kSweep >= 2)
-    sweepTileStage0<kSweep >= 3, kSweep == 4 || kSweep == 6, kSweep >= 5>(reinterpret_cast<const float *>(tile),
+    sweepTileStage0<kSweep >= 3, kSweep == 4>(reinterpret_cast<const float *>(tile),
                     scene.triExact + static_cast<size_t>(first) * 10, tileTris, tileTris, first, o, d, best);
   else if (kSweep == 1)
     sweepTilePrefiltered(reinterpret_cast<const double *>(tile), tileTris, tileTris, first, o, d, best);
@@ -776,9 +776,7 @@ __global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
     if (args.which != 1) {
       for (uint32_t j = 0; j < scene.numTiles; ++j) {
         const unsigned char *tile = stream.acquire();
-        if (args.sweep >= 5)
-          sweepStagedTile<6>(scene, tile, j, o, d, best);
-        else if (args.sweep == 4)
+        if (args.sweep == 4)
           sweepStagedTile<4>(scene, tile, j, o, d, best);
         else if (args.sweep == 3)
           sweepStagedTile<3>(scene, tile, j, o, d, best);
@@ -984,10 +982,6 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
   case 4: return launchKeyedConfig<256, 2, 4>(args, numSms, stream);
   case 24: return launchKeyedConfig<256, 3, 4>(args, numSms, stream);
   case 34: return launchKeyedConfig<192, 4, 4>(args, numSms, stream);
-  case 5: return launchKeyedConfig<256, 2, 5>(args, numSms, stream);   // 3 + pipelined survivor loop
-  case 25: return launchKeyedConfig<256, 3, 5>(args, numSms, stream);
-  case 6: return launchKeyedConfig<256, 2, 6>(args, numSms, stream);   // 4 + pipelined survivor loop
-  case 26: return launchKeyedConfig<256, 3, 6>(args, numSms, stream);
   case 33: return launchKeyedConfig<192, 4, 3>(args, numSms, stream);
   case 43: return launchKeyedConfig<128, 5, 3>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
