@@ -40,6 +40,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+_JSON_OUT = sys.stdout
 WIDTH, HEIGHT, SPP, SEED = 640, 480, int(os.environ.get("BENCH_SPP", "256")), 1  # BENCH_SPP: profiling only
 SCENE = "cornell"
 METRIC = "Msamples/sec on CornellBox 640x480"
@@ -186,7 +187,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
     return 0
 
 
@@ -354,11 +355,18 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     return 0
 
 
 def main():
+    # Rank 0 must print exactly ONE JSON line on stdout.  Libraries underneath (NCCL prints
+    # "NCCL version ..." on stdout at the first collective) must not add to it: park the real
+    # stdout, point fd 1 at stderr for the whole run, and write the JSON line to the parked fd.
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
