@@ -80,6 +80,24 @@ void basisFromZ(H3 z, H3 &xx, H3 &yy) {
   yy = hnormalised(hcross(z, xx));
 }
 
+// Owns the CUDA events of one call so that early error returns do not leak them.
+struct EventList {
+  std::vector<cudaEvent_t> events;
+  EventList() = default;
+  EventList(const EventList &) = delete;
+  EventList &operator=(const EventList &) = delete;
+  ~EventList() {
+    for (cudaEvent_t e : events)
+      cudaEventDestroy(e);
+  }
+  cudaError_t make(cudaEvent_t *out) {
+    const cudaError_t err = cudaEventCreate(out);
+    if (err == cudaSuccess)
+      events.push_back(*out);
+    return err;
+  }
+};
+
 template <typename T>
 struct DeviceBuffer {
   T *ptr{nullptr};
@@ -397,7 +415,7 @@ static int ensureFilter(PtContext *ctx, double originBound, uint64_t *launches) 
 // Launches the batches of one render call on ctx->stream; does not synchronise.
 static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderParams *params,
                          const PtRenderOptions *options, int passBegin, int numPasses,
-                         std::vector<cudaEvent_t> *events, uint64_t *launches) {
+                         EventList *owner, std::vector<cudaEvent_t> *events, uint64_t *launches) {
   const PtRenderOptions defaults{};
   const PtRenderOptions &opt = options ? *options : defaults;
   const int rowStep = opt.rowStep > 0 ? opt.rowStep : 1;
@@ -432,8 +450,8 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
     const int batch = static_cast<int>(std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses - done)));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (events) {
-      PT_CUDA(cudaEventCreate(&e0));
-      PT_CUDA(cudaEventCreate(&e1));
+      PT_CUDA(owner->make(&e0));
+      PT_CUDA(owner->make(&e1));
       PT_CUDA(cudaEventRecord(e0, ctx->stream));
     }
     if (sequential) {
@@ -518,14 +536,15 @@ int ptb200_context_render(PtContext *ctx, const PtCamera *camera, const PtRender
   ctx->accHeight = params->height;
   PT_CUDA(cudaMemsetAsync(ctx->counters.ptr + 1, 0, sizeof(unsigned long long), ctx->stream));
 
+  EventList owned;
   cudaEvent_t begin = nullptr, end = nullptr;
-  PT_CUDA(cudaEventCreate(&begin));
-  PT_CUDA(cudaEventCreate(&end));
-  std::vector<cudaEvent_t> events;
+  PT_CUDA(owned.make(&begin));
+  PT_CUDA(owned.make(&end));
+  std::vector<cudaEvent_t> events; // (start, stop) of every path-tracing kernel, owned by `owned`
   uint64_t launches = 0;
   PT_CUDA(cudaEventRecord(begin, ctx->stream));
   const int rc = enqueueRender(ctx, camera, params, options, options ? options->passBegin : 0,
-                               params->samplesPerPixel, &events, &launches);
+                               params->samplesPerPixel, &owned, &events, &launches);
   if (rc == PTB200_OK) {
     PT_CUDA(cudaEventRecord(end, ctx->stream));
     PT_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -553,10 +572,6 @@ int ptb200_context_render(PtContext *ctx, const PtCamera *camera, const PtRender
     stats->kernelMs = ms;
     stats->sweepKernelMs = sweepMs;
   }
-  for (cudaEvent_t e : events)
-    cudaEventDestroy(e);
-  cudaEventDestroy(begin);
-  cudaEventDestroy(end);
   return rc;
 }
 
@@ -802,9 +817,10 @@ int ptb200_measure_fp64_peak(int32_t device, double *tflops, double *millisecond
   DeviceBuffer<double> sink;
   PT_CUDA(sink.ensure(1));
   const int threads = 512, blocks = prop.multiProcessorCount * 4, iterations = 4096;
-  cudaEvent_t e0, e1;
-  PT_CUDA(cudaEventCreate(&e0));
-  PT_CUDA(cudaEventCreate(&e1));
+  EventList owned;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  PT_CUDA(owned.make(&e0));
+  PT_CUDA(owned.make(&e1));
   double best = 0, bestMs = 0;
   for (int rep = 0; rep < 5; ++rep) { // first repetitions warm up
     PT_CUDA(cudaEventRecord(e0, nullptr));
@@ -820,8 +836,6 @@ int ptb200_measure_fp64_peak(int32_t device, double *tflops, double *millisecond
       bestMs = ms;
     }
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   *tflops = best;
   if (milliseconds)
     *milliseconds = bestMs;

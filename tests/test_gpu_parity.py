@@ -230,7 +230,7 @@ def test_progress_callback_runs_on_calling_thread_with_partial_frames(scenes, ca
     assert np.array_equal(final["sum"], ref["sum"])
 
 
-def test_one_stage_sweep_config_renders_identically(scenes, tmp_path):
+def test_every_megakernel_configuration_renders_identically(scenes, tmp_path):
     """Every megakernel instantiation (sweep variant x launch shape, PTB200_KEYED_CONFIG) must give
     the same framebuffer and cast count bit for bit."""
     import os
