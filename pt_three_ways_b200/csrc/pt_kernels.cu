@@ -7,7 +7,10 @@
 //                           row-major order (Scene.cpp:208-220), primitives spread over lanes
 //   reducePassesKernel      per-pixel accumulation of per-pass samples IN PASS ORDER
 //                           (SampledPixel::accumulate, SampledPixel.cpp:3-6)
-//   intersectKernel         Scene::intersect/intersectSpheres/intersectTriangles for tests
+//   buildFilterKernel       FP32 copies + per-triangle error bounds for the stage-0 sweep
+//   intersectKernel         Scene::intersect/intersectSpheres/intersectTriangles for tests,
+//                           through every sweep variant
+//   auditStage0Kernel       test hook: stage 0 vs the exact test on every (ray, triangle) pair
 //   fp64PeakKernel          DFMA throughput probe (roofline denominator)
 #include "pt_kernels.h"
 
