@@ -347,6 +347,17 @@ def run_ours(args):
             },
         }
         if world == 1 and not args.no_cpu_baseline:
+            # The other RNG mode, for the record: the reference's exact mt19937 stream (one pass
+            # per warp, parallel over passes only) on a bounded sample of the same workload.
+            ew, eh = 160, 120
+            est = ctx.render(scene.camera(ew, eh), capi.make_params(ew, eh, spp=SPP, seed=SEED),
+                             capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL, device=local_rank))
+            line["exact_stream_mode"] = {
+                "value": est["samples"] / est["kernel_ms"] / 1e3, "unit": UNIT,
+                "sample": f"{SCENE} {ew}x{eh} (same aspect), {SPP} passes, PTB200_RNG_MT19937_SEQUENTIAL",
+                "parity": "bit-exact vs the oracle's sequential policy, which equals the reference's "
+                          "per-pass images (tests/test_oracle_golden.py)",
+                "note": "parallel over passes only (SURVEY.md section 0 item 3); not the timed headline"}
             threads = os.cpu_count() or 1
             v, info = cpu_reference_step(threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, **info,

@@ -48,10 +48,12 @@ __host__ __device__ inline uint32_t smemAfterTiles(uint32_t numSpheres, uint32_t
 // memory between the strata of a sample, [component][thread] so consecutive threads hit
 // consecutive banks; that keeps ~32 registers per thread free for a third resident CTA.
 constexpr uint32_t kPrimaryDoubles = 16;
+constexpr uint32_t kPendingDoubles = 8;   // the prefetched next sample, see the megakernel
+constexpr int kPrefetchBatch = 12;        // refill the prefetch slots when this many lanes' are empty
 __host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
                                uint32_t threadsForPrimarySlots) {
   return smemAfterTiles(numSpheres, tileTris, numTiles, sweep) +
-         static_cast<size_t>(threadsForPrimarySlots) * kPrimaryDoubles * sizeof(double);
+         static_cast<size_t>(threadsForPrimarySlots) * (kPrimaryDoubles + kPendingDoubles) * sizeof(double);
 }
 
 // Streams tiles cyclically (0,1,..,n-1,0,1,..) through two buffers with TMA bulk copies.
@@ -207,6 +209,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   // The camera ray's hit stays alive across its numSub sub-paths: in shared memory.
   double *const primarySlot = reinterpret_cast<double *>(smemRaw + smemAfterTiles(scene.numSpheres, scene.tileTris,
                                                                                   scene.numTiles, kSweep)) + threadIdx.x;
+  // ... and so does this lane's prefetched next sample (6 doubles of ray + slot + key/pixel).
+  double *const pendingSlot = primarySlot + kPrimaryDoubles * kBlock;
+  bool pendingValid = false, exhausted = false;
   uint32_t primaryMaterial = 0;
   bool primarySpecular = false;
   int subPath = 0;
@@ -216,46 +221,65 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   bool stackSpecular[kMaxDepth];
 
   for (;;) {
-    // ---- 1. lanes without a path pull the next (pass, pixel) ticket, warp-aggregated ----
-    const unsigned wantMask = __ballot_sync(kFullMask, mode == kNeedWork);
-    bool newSample = false;
-    if (wantMask) {
+    // ---- 1. tickets and camera rays, prefetched in batches ----
+    // A camera ray costs ~400 instructions whether 1 or 32 lanes need one.  So every lane keeps
+    // ONE prefetched sample (ticket + camera ray) parked in shared memory; slots are refilled
+    // together once kPrefetchBatch of them are empty (or a lane is out of work right now).
+    const bool slotEmpty = !pendingValid && !exhausted;
+    const unsigned emptyMask = __ballot_sync(kFullMask, slotEmpty);
+    const unsigned starvingMask = __ballot_sync(kFullMask, slotEmpty && mode == kNeedWork);
+    if (emptyMask && (starvingMask || __popc(emptyMask) >= kPrefetchBatch)) {
       unsigned long long base = 0;
-      const int leader = __ffs(wantMask) - 1;
+      const int leader = __ffs(emptyMask) - 1;
       if (static_cast<int>(lane) == leader)
-        base = atomicAdd(args.ticket, static_cast<unsigned long long>(__popc(wantMask)));
+        base = atomicAdd(args.ticket, static_cast<unsigned long long>(__popc(emptyMask)));
       base = __shfl_sync(kFullMask, base, leader);
-      if (mode == kNeedWork) {
-        const unsigned long long item = base + __popc(wantMask & ((1u << lane) - 1u));
+      if (slotEmpty) {
+        const unsigned long long item = base + __popc(emptyMask & ((1u << lane) - 1u));
         if (item < args.totalItems) {
           const uint32_t passInBatch = static_cast<uint32_t>(item / args.ownPixels);
           const uint32_t own = static_cast<uint32_t>(item % args.ownPixels);
-          const uint32_t row = own / args.width;
           const int px = static_cast<int>(own % args.width);
-          const int py = args.rowBegin + static_cast<int>(row) * args.rowStep;
-          pixel = static_cast<uint32_t>(px) + static_cast<uint32_t>(py) * args.width;
-          sampleSlot = item;
-          key0 = static_cast<uint32_t>(args.seed + args.passBegin + static_cast<int>(passInBatch));
-          depth = 0;
+          const int py = args.rowBegin + static_cast<int>(own / args.width) * args.rowStep;
+          const uint32_t nextPixel = static_cast<uint32_t>(px) + static_cast<uint32_t>(py) * args.width;
+          const uint32_t nextKey = static_cast<uint32_t>(args.seed + args.passBegin + static_cast<int>(passInBatch));
           if (args.maxDepth <= 0) { // radiance() returns Vec3() before intersecting (Scene.cpp:128-129)
-            args.samples[3 * sampleSlot + 0] = 0.0;
-            args.samples[3 * sampleSlot + 1] = 0.0;
-            args.samples[3 * sampleSlot + 2] = 0.0;
+            args.samples[3 * item + 0] = 0.0;
+            args.samples[3 * item + 1] = 0.0;
+            args.samples[3 * item + 2] = 0.0;
           } else {
-            mode = kTracing;
-            newSample = true;
+            V3 o, d;
+            keyedCameraRay(args.camera, nextKey, nextPixel, px, py, o, d);
+            pendingSlot[0 * kBlock] = o.x;
+            pendingSlot[1 * kBlock] = o.y;
+            pendingSlot[2 * kBlock] = o.z;
+            pendingSlot[3 * kBlock] = d.x;
+            pendingSlot[4 * kBlock] = d.y;
+            pendingSlot[5 * kBlock] = d.z;
+            pendingSlot[6 * kBlock] = __longlong_as_double(static_cast<long long>(item));
+            pendingSlot[7 * kBlock] = __hiloint2double(static_cast<int>(nextKey), static_cast<int>(nextPixel));
+            pendingValid = true;
           }
         } else {
-          mode = kFinished;
+          exhausted = true;
         }
       }
     }
     __syncwarp();
-    if (newSample) { // all lanes that start a sample this iteration generate their camera rays together
-      const uint32_t own = static_cast<uint32_t>(sampleSlot % args.ownPixels);
-      const int px = static_cast<int>(own % args.width);
-      const int py = args.rowBegin + static_cast<int>(own / args.width) * args.rowStep;
-      keyedCameraRay(args.camera, key0, pixel, px, py, origin, direction);
+    if (mode == kNeedWork) {
+      if (pendingValid) { // start the prefetched sample
+        origin = mk(pendingSlot[0 * kBlock], pendingSlot[1 * kBlock], pendingSlot[2 * kBlock]);
+        direction = mk(pendingSlot[3 * kBlock], pendingSlot[4 * kBlock], pendingSlot[5 * kBlock]);
+        sampleSlot = static_cast<uint64_t>(__double_as_longlong(pendingSlot[6 * kBlock]));
+        const double packed = pendingSlot[7 * kBlock];
+        key0 = static_cast<uint32_t>(__double2hiint(packed));
+        pixel = static_cast<uint32_t>(__double2loint(packed));
+        pendingValid = false;
+        depth = 0;
+        mode = kTracing;
+      } else if (exhausted) {
+        mode = kFinished;
+      }
     }
     const bool tracing = mode == kTracing;
     if (resident) {
@@ -396,15 +420,26 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         u = args.firstBounceUPow2 ? su * args.invFirstBounceU : ieeeDiv(su, static_cast<double>(args.firstBounceU));
         v = args.firstBounceVPow2 ? sv * args.invFirstBounceV : ieeeDiv(sv, static_cast<double>(args.firstBounceV));
       }
-      bool specular;
-      V3 newDirection;
-      if (rp < surface.reflectivity) {
-        newDirection = coneSample(reflect(surface.normal, surface.incoming),
-                                  materialOf(scene, surface.material).coneAngle(), u, v);
-        specular = true;
+      // coneSample() / hemisphereSample() (Samples.cpp:6-30) end in the same
+      // normalised(basis.transform(cos(t)*r, sin(t)*r, z)): the few specular lanes only prepare
+      // its inputs, then every bouncing lane runs that tail together.
+      const bool specular = rp < surface.reflectivity;
+      Basis frame{surface.basisX, surface.basisY, surface.normal};
+      double angle = (2 * kPi) * u, radius = 0, zScale = 0;
+      bool direct = false;
+      V3 newDirection = mk(0, 0, 0);
+      if (specular) {
+        newDirection = reflect(surface.normal, surface.incoming);
+        direct = coneSampleSetup(newDirection, materialOf(scene, surface.material).coneAngle(), u, v, frame,
+                                 angle, radius, zScale);
       } else {
-        newDirection = hemisphereSample(Basis{surface.basisX, surface.basisY, surface.normal}, u, v);
-        specular = false;
+        radius = ieeeSqrt(v);
+        zScale = ieeeSqrt(1 - v);
+      }
+      if (!direct) {
+        double sinT, cosT;
+        sinCos(angle, sinT, cosT);
+        newDirection = normalised(transform(frame, mk(cosT * radius, sinT * radius, zScale)));
       }
       if (fromPrimary) {
         primarySpecular = specular;

@@ -197,6 +197,22 @@ static __device__ __noinline__ V3 coneSample(V3 direction, double coneTheta, dou
   const Basis basis = basisFromZ(direction);
   return normalised(transform(basis, mk(cosT * radius, sinT * radius, zScale)));
 }
+// The specular-only part of coneSample(): everything up to the final
+// normalised(basis.transform(cos(t)*r, sin(t)*r, z)), which has the same shape as
+// hemisphereSample()'s and is therefore executed once, by specular and diffuse lanes together,
+// in the megakernel.  Returns true when the cone is degenerate and `direction` is the answer.
+static __device__ __noinline__ bool coneSampleSetup(V3 direction, double coneTheta, double u, double v,
+                                                    Basis &basis, double &randomTheta, double &radius,
+                                                    double &zScale) {
+  if (coneTheta < kEpsilon)
+    return true;
+  coneTheta = coneTheta * (1.0 - ieeeDiv(2.0 * arcCos(u), kPi));
+  sinCos(coneTheta, radius, zScale);
+  randomTheta = v * 2 * kPi;
+  basis = basisFromZ(direction);
+  return false;
+}
+
 // hemisphereSample (src/math/Samples.cpp:21-30).
 __device__ __forceinline__ V3 hemisphereSample(const Basis &basis, double u, double v) {
   const double theta = (2 * kPi) * u;
