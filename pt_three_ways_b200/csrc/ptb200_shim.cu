@@ -45,8 +45,11 @@ int fail(int code, const char *format, ...) {
       return fail(PTB200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(ptErr_));             \
   } while (0)
 
-constexpr size_t kResidentTileBytes = 100 * 1024; // one tile per CTA, two CTAs per SM
-constexpr size_t kStreamTileBytes = 50 * 1024;    // two buffers of this per CTA when streaming
+// Tile plan, in bytes of FP64 sweep data (72 B/triangle; the FP32 stage-0 tile is 56 B/triangle).
+// Budget: two CTAs per SM must fit in 227 KB, each with its tile buffer(s) plus 48 KB of
+// per-thread slots (primary hit + prefetched sample, 192 B x 256 threads).
+constexpr size_t kResidentTileBytes = 72 * 1024; // <= 1024 triangles: one resident tile per CTA
+constexpr size_t kStreamTileBytes = 40 * 1024;   // larger scenes: two buffers of <= 568 triangles
 constexpr size_t kSampleBufferBytes = size_t(4) << 30;
 
 // ---- host restatement of the per-triangle values the reference derives in addTriangle ----
