@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
 
   // ---- per-lane path state ----
   int mode = kNeedWork;
-  uint64_t casts = 0;
+  uint32_t casts = 0;            // per lane and launch: far below 2^32
   uint64_t sampleSlot = 0;       // where this sample's colour goes
   uint32_t pixel = 0;            // x + y*width (RNG key and framebuffer index)
   uint32_t key0 = 0;
@@ -457,11 +457,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   if (!resident)
     stream.drain();
   // one atomic per warp for the cast counter
+  unsigned long long warpCasts = casts;
 #pragma unroll 1
   for (int offset = 16; offset > 0; offset >>= 1)
-    casts += __shfl_down_sync(kFullMask, casts, offset);
-  if (lane == 0 && casts)
-    atomicAdd(args.castCounter, static_cast<unsigned long long>(casts));
+    warpCasts += __shfl_down_sync(kFullMask, warpCasts, offset);
+  if (lane == 0 && warpCasts)
+    atomicAdd(args.castCounter, warpCasts);
 }
 
 // =============================================================================================
@@ -990,7 +991,7 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
 //                   3 the same with the packed FP32x2 datapath (FFMA2); 4 = 3 + stage 0 also
 //                   rejects triangles certainly behind the ray (pays off on small scenes)
 //   launch shapes:  0 = 256 threads x 2 CTAs/SM (128 registers); 1 = 384 x 1 (168 registers);
-//                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5
+//                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5; 5 = 192 x 3
 // Default (measured on B200, profiles/): packed FP32 stage 0 everywhere it is usable; three CTAs
 // per SM for small scenes, where shading latency rather than the sweep limits the kernel.
 // PTB200_KEYED_CONFIG overrides it (tools/sweep_configs.py).
@@ -1022,6 +1023,8 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
   case 34: return launchKeyedConfig<192, 4, 4>(args, numSms, stream);
   case 33: return launchKeyedConfig<192, 4, 3>(args, numSms, stream);
   case 43: return launchKeyedConfig<128, 5, 3>(args, numSms, stream);
+  case 54: return launchKeyedConfig<192, 3, 4>(args, numSms, stream);
+  case 44: return launchKeyedConfig<128, 5, 4>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
 }
