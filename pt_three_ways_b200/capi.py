@@ -81,6 +81,15 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
+            # Build in-tree if a CUDA toolchain is at hand (a fresh checkout); otherwise fail
+            # loudly: there is no CPU or Python implementation to fall back to.
+            import shutil
+            import subprocess
+            if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+                env = dict(os.environ, PATH=os.environ.get("PATH", "") + ":/usr/local/cuda/bin")
+                subprocess.run(["make", "-C", os.path.join(PACKAGE_DIR, "csrc")], check=False,
+                               capture_output=True, env=env)
+        if not os.path.exists(LIB_PATH):
             raise ImportError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
                 "g.build()'` or `make -C pt_three_ways_b200/csrc` (no CPU fallback exists)")
