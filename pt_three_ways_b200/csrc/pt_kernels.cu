@@ -517,6 +517,29 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
     const uint32_t hi = next(lane);
     return canonicalFromWords(lo, hi);
   }
+  __device__ __forceinline__ static uint32_t temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  // Three canonical doubles (six outputs) at once: when they do not straddle a refill the six
+  // state words are read independently instead of through six dependent next() calls.
+  __device__ __forceinline__ void canonical3(unsigned lane, double &a, double &b, double &c) {
+    if (index + 6 <= 624) {
+      const uint32_t w0 = temper(state[index]), w1 = temper(state[index + 1]), w2 = temper(state[index + 2]),
+                     w3 = temper(state[index + 3]), w4 = temper(state[index + 4]), w5 = temper(state[index + 5]);
+      index += 6;
+      a = canonicalFromWords(w0, w1);
+      b = canonicalFromWords(w2, w3);
+      c = canonicalFromWords(w4, w5);
+    } else {
+      a = canonical(lane);
+      b = canonical(lane);
+      c = canonical(lane);
+    }
+  }
   // Discards `count` outputs.
   __device__ __forceinline__ void skip(uint32_t count, unsigned lane) {
     while (count) {
@@ -528,18 +551,6 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
     }
   }
 };
-
-// (t, sphere-before-triangle, index) ordering of the serial scans (Scene.cpp:33,94,118-121).
-__device__ __forceinline__ bool nearerThan(const Nearest &a, const Nearest &b) {
-  if (a.t != b.t)
-    return a.t < b.t;
-  const bool aSphere = a.prim < 0, bSphere = b.prim < 0;
-  if (aSphere != bSphere)
-    return aSphere;
-  if (aSphere)
-    return a.prim > b.prim; // -(i+1): larger is the lower sphere index
-  return a.prim < b.prim;
-}
 
 // Whole-warp Scene::intersect: lanes stride the primitive lists, then an argmin.
 __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o, V3 d, unsigned lane,
@@ -567,33 +578,36 @@ __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o,
     }
   }
   if (useTriangles) {
-    // A triangle only replaces a sphere hit when strictly nearer, which the ordering in
-    // nearerThan() encodes; per lane the strict `<` keeps the lowest index among equals.
-    for (uint32_t tile = 0; tile < scene.numTiles; ++tile) {
-      const double *base = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris;
-      // Padding triangles are all-zero (det == 0) and reject themselves.  (Unrolling this loop
-      // by two was measured: 10 % slower, profiles/seq_r1j.jsonl.)
+    // A triangle only replaces a sphere hit when strictly nearer, which the argmin's ordering
+    // below encodes; per lane the strict `<` keeps the lowest index among equals.
+    // One 80-byte AoS record per triangle (triExact); padding records are all-zero (det == 0)
+    // and reject themselves.  (Unrolling this loop by two was measured: 10 % slower.)
+    const uint32_t slots = scene.numTiles * scene.tileTris;
 #pragma unroll 1
-      for (uint32_t i = lane; i < scene.tileTris; i += 32) {
-        const uint32_t index = tile * scene.tileTris + i;
-        const V3 v0 = mk(__ldg(base + 0 * scene.tileTris + i), __ldg(base + 1 * scene.tileTris + i),
-                         __ldg(base + 2 * scene.tileTris + i));
-        const V3 e1 = mk(__ldg(base + 3 * scene.tileTris + i), __ldg(base + 4 * scene.tileTris + i),
-                         __ldg(base + 5 * scene.tileTris + i));
-        const V3 e2 = mk(__ldg(base + 6 * scene.tileTris + i), __ldg(base + 7 * scene.tileTris + i),
-                         __ldg(base + 8 * scene.tileTris + i));
-        testTriangle(v0, e1, e2, o, d, static_cast<int>(index), best);
-      }
+    for (uint32_t index = lane; index < slots; index += 32) {
+      const double2 *record = reinterpret_cast<const double2 *>(scene.triExact + 10 * static_cast<size_t>(index));
+      const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
+                    a4 = __ldg(record + 4);
+      testTriangle(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d,
+                   static_cast<int>(index), best);
     }
   }
-  for (int offset = 16; offset > 0; offset >>= 1) {
-    Nearest other;
-    other.t = __shfl_xor_sync(kFullMask, best.t, offset);
-    other.det = __shfl_xor_sync(kFullMask, best.det, offset);
-    other.prim = __shfl_xor_sync(kFullMask, best.prim, offset);
-    if (other.prim != kNoPrim && (best.prim == kNoPrim || nearerThan(other, best)))
-      best = other;
-  }
+  // Warp argmin in the serial scans' order (t, sphere-before-triangle, index) with three
+  // integer min-reductions: hit distances are positive, so their bit patterns order like
+  // unsigned integers.
+  const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(best.t));
+  const uint32_t hi = static_cast<uint32_t>(bits >> 32), lo = static_cast<uint32_t>(bits);
+  const uint32_t minHi = __reduce_min_sync(kFullMask, hi);
+  const uint32_t minLo = __reduce_min_sync(kFullMask, hi == minHi ? lo : 0xffffffffu);
+  const bool nearest = hi == minHi && lo == minLo;
+  const uint32_t order = best.prim == kNoPrim ? 0xffffffffu
+                         : best.prim < 0      ? static_cast<uint32_t>(-best.prim - 1)
+                                              : 0x40000000u + static_cast<uint32_t>(best.prim);
+  const uint32_t minOrder = __reduce_min_sync(kFullMask, nearest ? order : 0xffffffffu);
+  const int winner = __ffs(__ballot_sync(kFullMask, nearest && order == minOrder)) - 1;
+  best.t = __shfl_sync(kFullMask, best.t, winner);
+  best.det = __shfl_sync(kFullMask, best.det, winner);
+  best.prim = __shfl_sync(kFullMask, best.prim, winner);
   return best;
 }
 
@@ -708,9 +722,8 @@ __global__ void __launch_bounds__(kWarps * 32)
         const bool fromPrimary = depth == 0;
         if (fromPrimary)
           surface = primary;
-        const double ru = rng.canonical(lane); // u, v, p in this order (Scene.cpp:157-161)
-        const double rv = rng.canonical(lane);
-        const double rp = rng.canonical(lane);
+        double ru, rv, rp; // u, v, p in this order (Scene.cpp:157-161)
+        rng.canonical3(lane, ru, rv, rp);
         double u = ru, v = rv;
         if (fromPrimary) {
           u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
