@@ -293,3 +293,49 @@ def test_reference_dod_tests_through_the_cpp_adaptor():
                          capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert " 0 failures" in res.stdout and "GPU KATs ran" in res.stdout
+
+
+# ---- random scenes: every shading branch (mirror, glossy, Fresnel, emitters, inside spheres) ---
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_scene_intersections_match_oracle(seed, oracle, capi):
+    from tests import random_scenes
+    scene = random_scenes.random_scene(seed, num_triangles=70)
+    rays = random_scenes.rays_for(scene, 4000, seed + 20)
+    want = oracle.OracleScene(scene).intersect(rays)
+    for sweep in (capi.SWEEP_ONE_STAGE, capi.SWEEP_TWO_STAGE_FP64, capi.SWEEP_FP32_STAGE0,
+                  capi.SWEEP_FP32X2_STAGE0, capi.SWEEP_FP32X2_STAGE0_T):
+        assert_hits_equal(capi.intersect(scene, rays, sweep=sweep), want)
+    assert_hits_equal(capi.intersect(scene, rays, warp_cooperative=True), want)
+    audit = capi.audit_stage0(scene, rays)
+    assert audit["violations"] == 0 and audit["accepts"] > 0
+
+
+@pytest.mark.parametrize("mode_name", ["keyed", "sequential"])
+@pytest.mark.parametrize("seed,kw", [(4, {}), (5, dict(first_u=3, first_v=2, max_depth=7)), (6, dict(max_depth=2)),
+                                     (8, dict(first_u=1, first_v=1, max_depth=12))])
+def test_random_scene_renders_match_oracle(seed, kw, mode_name, oracle, capi):
+    from tests import random_scenes
+    mode = capi.RNG_KEYED_PHILOX if mode_name == "keyed" else capi.RNG_MT19937_SEQUENTIAL
+    scene = random_scenes.random_scene(seed, num_triangles=25, num_spheres=3)
+    w, h, spp = 28, 21, 3
+    cam = scene.camera(w, h)
+    got, st = capi.render(scene, cam, capi.make_params(w, h, spp=spp, seed=13, **kw), capi.make_options(rng_mode=mode))
+    want = oracle.OracleScene(scene).render(cam, oracle.params_array(w, h, spp=spp, seed=13, **kw), mode, threads=4)
+    assert st["casts"] == want["casts"]
+    assert np.array_equal(got["sum"], want["sums"])  # bit-exact
+    assert np.array_equal(got["n"], want["counts"])
+
+
+def test_camera_without_aperture_draws_two_numbers(oracle, capi):
+    """Camera::rayFromUnit returns before drawing the lens sample when apertureRadius == 0
+    (Camera.h:26-27): the sequential stream must then be two draws shorter per pixel."""
+    from tests import random_scenes
+    scene = random_scenes.random_scene(9, num_triangles=10, num_spheres=2)
+    scene.camera64x48 = random_scenes.camera18((0, 0, -5), (0, 0, 0), (0, 1, 0), 64, 48, 40.0)
+    w, h = 20, 15
+    cam = scene.camera(w, h)
+    assert cam[16] == 0.0
+    for mode in (capi.RNG_KEYED_PHILOX, capi.RNG_MT19937_SEQUENTIAL):
+        got, _ = capi.render(scene, cam, capi.make_params(w, h, spp=2, seed=5), capi.make_options(rng_mode=mode))
+        want = oracle.OracleScene(scene).render(cam, oracle.params_array(w, h, spp=2, seed=5), mode)
+        assert np.array_equal(got["sum"], want["sums"])
