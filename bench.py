@@ -116,7 +116,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline
 # ---------------------------------------------------------------------------------------------
-def cpu_reference_step(threads, width=320, height=240):
+def cpu_reference_step(threads, width=256, height=192):
     """One bounded sample of the workload on the host: same scene, same aspect ratio, reduced
     resolution, spp = 2 x threads so the reference's own pass scheduler (one std::async task
     per pass, Scene.cpp:208-229) has two waves of work.  Returns (Msamples/s, info)."""
