@@ -302,11 +302,13 @@ def run_ours(args):
     logical_gbs = casts_per_step_rank * scene.sweep_bytes() / (sweep_ms_per_launch * 1e-3) / 1e9
     fp64_tflops = casts_per_step_rank * scene.sweep_flops() / (sweep_ms_per_launch * 1e-3) / 1e12
     fp64_peak, _ = capi.measure_fp64_peak(local_rank)
-    traffic = None
+    traffic, ncu_capture = None, None
     ncu_summary = os.path.join(ROOT, "profiles", "ncu_summary.json")
     if os.path.exists(ncu_summary):
         try:
-            traffic = json.load(open(ncu_summary)).get("dram_bytes_per_launch")
+            summary = json.load(open(ncu_summary))
+            traffic = summary.get("dram_bytes_per_launch")
+            ncu_capture = summary.get("latest_full_capture")  # committed ncu figures, not measured now
         except Exception:
             traffic = None
 
@@ -344,6 +346,7 @@ def run_ours(args):
                          "peak_source": "self-measured DFMA loop (ptb200_measure_fp64_peak)",
                          "flops_per_cast": scene.sweep_flops()},
                 "ms_per_launch": sweep_ms_per_launch, "bytes_per_cast": scene.sweep_bytes(),
+                "ncu": ncu_capture,
             },
         }
         if world == 1 and not args.no_cpu_baseline:
