@@ -11,12 +11,17 @@ constexpr int kMaxDepth = 64;        // deepest supported RenderParams::maxDepth
 constexpr uint32_t kFullMask = 0xffffffffu;
 
 // ---- layout in HBM --------------------------------------------------------------------------
-// Triangle sweep data is tile-major SoA: tile j holds 9 arrays of `tileTris` doubles
-// (v0x v0y v0z e1x e1y e1z e2x e2y e2z), contiguous, so one TMA bulk copy stages a whole tile
-// into shared memory and a warp that reads triangle i of every array issues 16-byte broadcast
-// loads.  e1 = v1-v0 and e2 = v2-v0 are what TriangleVertices::uVector()/vVector()
-// (TriangleVertices.h:25-31) recompute on every call; storing them is bit-identical.
-// Tiles are padded with all-zero triangles (det == 0 -> skipped, Scene.cpp:66-68).
+// Triangle data exists in three layouts, all holding v0, e1 = v1-v0, e2 = v2-v0 (what
+// TriangleVertices::uVector()/vVector(), TriangleVertices.h:25-31, recompute on every call;
+// storing them is bit-identical), padded per tile with all-zero triangles (det == 0 ->
+// skipped, Scene.cpp:66-68):
+//   triSweep   FP64, tile-major SoA (9 arrays of `tileTris` doubles per tile): what the FP64
+//              sweep variants stage into shared memory with one TMA bulk copy per tile; every
+//              lane of a warp reads the same triangle, i.e. 16-byte broadcast loads;
+//   triFilter  FP32 copies + error bounds, blocked by four triangles: what the default FP32
+//              stage-0 sweep stages into shared memory (same TMA path);
+//   triExact   FP64 AoS records for the exact test of stage-0 survivors and for the sequential
+//              kernel's lane-strided sweep (global memory / L1).
 struct DeviceScene {
   const double *triSweep;     // [numTiles][9][tileTris]
   const double4 *triShade;    // [numTriangles][4] {normal xyz, material} {frontX xyz, frontY.x}

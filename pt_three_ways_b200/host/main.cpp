@@ -9,6 +9,7 @@
 #include "ArrayOutput.h"
 #include "HostApi.h"
 #include "PngWriter.h"
+#include "Progressifier.h"
 #include "Scene.h"
 #include "SceneRecipes.h"
 
@@ -166,7 +167,12 @@ int main(int argc, const char *argv[]) {
     using namespace std::chrono_literals;
     const auto every = std::chrono::seconds(saveEvery);
     auto nextSave = std::chrono::system_clock::now() + every;
+    // The reference prints progress from inside render() (Scene.cpp:233,244); the GPU backend
+    // reports after each collected batch of passes, through the same updateFunc.
+    Progressifier progressifier(static_cast<size_t>(renderParams.samplesPerPixel));
+    const size_t pixelCount = static_cast<size_t>(renderParams.width) * static_cast<size_t>(renderParams.height);
     auto throttledSave = [&](ArrayOutput &output) { // main.cpp:331-343
+      progressifier.update(output.totalSamples() / pixelCount);
       if (every == 0s)
         return;
       const auto now = std::chrono::system_clock::now();
