@@ -265,8 +265,10 @@ inline bool intersectSpheres(const Scene &scene, V3 origin, V3 direction, double
   return true;
 }
 
+// fpWay: fp::Triangle::intersect (src/fp/Triangle.cpp:9-41) is the same arithmetic, but rejects
+// `t < Epsilon` where Scene.cpp:93 accepts `t > Epsilon`: t == Epsilon exactly is a hit there.
 inline bool intersectTriangles(const Scene &scene, V3 origin, V3 direction, double nearerThan,
-                               HitRecord &out) { // Scene.cpp:52-113
+                               HitRecord &out, bool fpWay = false) { // Scene.cpp:52-113
   double currentNearestDist = nearerThan;
   int nearestIndex = -1;
   double nearestDet = 0;
@@ -284,7 +286,7 @@ inline bool intersectTriangles(const Scene &scene, V3 origin, V3 direction, doub
     if ((u < 0.0) | (u > 1.0) | (v < 0.0) | (u + v > 1)) // Unpredictable::any, Scene.cpp:89
       continue;
     const double t = dot(tri.e2, qVec) * invDet;
-    if (t > Epsilon && t < currentNearestDist) {
+    if ((fpWay ? t >= Epsilon : t > Epsilon) && t < currentNearestDist) {
       nearestIndex = static_cast<int>(i);
       nearestDet = det;
       currentNearestDist = t;
@@ -301,15 +303,20 @@ inline bool intersectTriangles(const Scene &scene, V3 origin, V3 direction, doub
   return true;
 }
 
+// fpWay: fp::intersect (src/fp/Render.cpp:36-46) walks ONE primitive list in insertion order and
+// keeps the strictly nearest hit.  The flat scene of this interface keeps triangles and spheres
+// in separate arrays, so an exact distance tie between a sphere and a triangle resolves to the
+// sphere here whatever the insertion order was (ties within a kind resolve to the lower index
+// in both); the nearest distance itself is order-independent.
 inline bool intersect(const Scene &scene, V3 origin, V3 direction, HitRecord &out,
-                      Counters &counters) { // Scene.cpp:115-122
+                      Counters &counters, bool fpWay = false) { // Scene.cpp:115-122
   counters.casts++;
   HitRecord sphereRec, triangleRec;
   const bool hitSphere = intersectSpheres(scene, origin, direction,
                                           std::numeric_limits<double>::infinity(), sphereRec);
   const bool hitTriangle = intersectTriangles(
       scene, origin, direction,
-      hitSphere ? sphereRec.distance : std::numeric_limits<double>::infinity(), triangleRec);
+      hitSphere ? sphereRec.distance : std::numeric_limits<double>::infinity(), triangleRec, fpWay);
   if (hitTriangle) {
     out = triangleRec;
     return true;
@@ -383,7 +390,7 @@ constexpr uint32_t PhiloxKeyHigh = 0xB200D0D0u;
 // One generator object per pass; a "site" (pixel, subPath, depth) is announced before each
 // group of draws.  The sequential policy ignores sites.
 struct Rng {
-  int mode; // 0 keyed Philox, 1 mt19937 sequential
+  int mode; // 0 keyed Philox, 1 mt19937 sequential (one per pass), 2 mt19937 per sample (fp way)
   Mt19937 mt;
   uint32_t key0;
   uint32_t pixel{0}, subPath{0}, level{0}, call{0};
@@ -393,12 +400,13 @@ struct Rng {
 
   Rng(int mode_, uint32_t passSeed, Counters *c) : mode(mode_), mt(passSeed), key0(passSeed), counters(c) {}
 
+  void reseed(uint32_t seed) { mt = Mt19937(seed); } // mode 2: a fresh engine per (pass, pixel)
   void site(uint32_t pixel_, uint32_t subPath_, uint32_t level_) {
     pixel = pixel_; subPath = subPath_; level = level_; call = 0; bufferedLeft = 0;
   }
   uint32_t word() {
     counters->rngWords++;
-    if (mode == 1)
+    if (mode != 0)
       return mt.next();
     if (bufferedLeft == 0) {
       philox4x32_10(pixel, subPath, level, call++, key0, PhiloxKeyHigh, buffered);
@@ -554,6 +562,67 @@ V3 radiance(const Scene &scene, Rng &rng, uint32_t pixel, uint32_t subPath, V3 o
   return scale(result, reciprocal);
 }
 
+// fp::radiance + radianceAtIntersection (src/fp/Render.cpp:48-118): the same estimator as
+// Scene::radiance with three differences that change the numbers:
+//   * the strata are walked v-major (cartesian_product(ints(0,numV), ints(0,numU)), :109-110),
+//     each drawing u, then v (toUVSample, :97-102), then p (:116);
+//   * a sub-sample contributes  radiance(child)  or  diffuse * radiance(child)  WITHOUT the
+//     emission (:66-73); the emission is added once, after the average:
+//     emission + sum / (numU*numV)  (:118);
+//   * hits come from fp::intersect (see intersect() above).
+V3 radianceFp(const Scene &scene, Rng &rng, V3 origin, V3 direction, int depth, const Params &params,
+              Counters &counters) {
+  const int numUSamples = depth == 0 ? params.firstBounceUSamples : 1;
+  const int numVSamples = depth == 0 ? params.firstBounceVSamples : 1;
+  if (depth >= params.maxDepth)
+    return V3{0, 0, 0};
+  HitRecord hit;
+  if (!intersect(scene, origin, direction, hit, counters, true))
+    return scene.environment;
+  const Material &mat = scene.materials[hit.material];
+  if (params.preview)
+    return mat.diffuse;
+  const Basis basis = basisFromZ(hit.normal);
+  const double iorFrom = hit.inside ? mat.indexOfRefraction : 1.0;
+  const double iorTo = hit.inside ? 1.0 : mat.indexOfRefraction;
+  const double reflectivity =
+      mat.reflectivity < 0 ? reflectance(hit.normal, direction, iorFrom, iorTo) : mat.reflectivity;
+  V3 incomingLight{0, 0, 0}; // accumulate(..., Vec3()): init = init + element, in order
+  for (int vSample = 0; vSample < numVSamples; ++vSample) {
+    for (int uSample = 0; uSample < numUSamples; ++uSample) {
+      const double u = (static_cast<double>(uSample) + rng.uniform(0, 1.0)) /
+                       static_cast<double>(numUSamples);
+      const double v = (static_cast<double>(vSample) + rng.uniform(0, 1.0)) /
+                       static_cast<double>(numVSamples);
+      const double p = rng.uniform(0, 1.0);
+      if (p < reflectivity) {
+        const V3 newDir =
+            coneSample(reflect(hit.normal, direction), mat.reflectionConeAngleRadians, u, v);
+        incomingLight = add(incomingLight, radianceFp(scene, rng, hit.position, newDir, depth + 1,
+                                                      params, counters));
+      } else {
+        const V3 newDir = hemisphereSample(basis, u, v);
+        const V3 child = radianceFp(scene, rng, hit.position, newDir, depth + 1, params, counters);
+        incomingLight = add(incomingLight, V3{mat.diffuse.x * child.x, mat.diffuse.y * child.y,
+                                              mat.diffuse.z * child.z});
+      }
+    }
+  }
+  const double reciprocal = 1.0 / static_cast<double>(numUSamples * numVSamples); // Vec3.h:51-54
+  return {std::fma(incomingLight.x, reciprocal, mat.emission.x),
+          std::fma(incomingLight.y, reciprocal, mat.emission.y),
+          std::fma(incomingLight.z, reciprocal, mat.emission.z)};
+}
+
+// The engine seed of fp::renderWholeScreen's renderOnePixel (src/fp/Render.cpp:125-126):
+// height*width*seed + x*width + y  — x*width, not y*width: the reference's own indexing —
+// evaluated in size_t and reduced mod 2^32 by mersenne_twister_engine::seed.
+inline uint32_t fpPixelSeed(const Params &params, int passSeed, int x, int y) {
+  const uint64_t frame = static_cast<uint64_t>(static_cast<int64_t>(params.height * params.width));
+  const uint64_t within = static_cast<uint64_t>(static_cast<int64_t>(x * params.width + y));
+  return static_cast<uint32_t>(frame * static_cast<uint64_t>(static_cast<int64_t>(passSeed)) + within);
+}
+
 // One pass of Scene::render's lambda (Scene.cpp:208-220): per-pixel colours of pass `s`,
 // rows [rowBegin, height) stepping rowStep for the keyed policy (the sequential policy
 // must walk every pixel; rows outside the selection are traced but not stored).
@@ -562,14 +631,18 @@ void renderPass(const Scene &scene, const Camera &cam, const Params &params, int
   Rng rng(rngMode, static_cast<uint32_t>(params.seed + pass), &counters);
   for (int y = 0; y < params.height; ++y) {
     const bool selected = y >= rowBegin && (y - rowBegin) % rowStep == 0;
-    if (!selected && rngMode == 0)
+    if (!selected && rngMode != 1)
       continue;
     for (int x = 0; x < params.width; ++x) {
       const uint32_t pixel = static_cast<uint32_t>(x + y * params.width);
       rng.site(pixel, 0, 0);
+      if (rngMode == 2) // fp::renderWholeScreen: one engine per pixel of the pass
+        rng.reseed(fpPixelSeed(params, params.seed + pass, x, y));
       V3 origin, direction;
       cameraRandomRay(cam, x, y, rng, origin, direction);
-      const V3 colour = radiance(scene, rng, pixel, 0, origin, direction, 0, params, counters);
+      const V3 colour = rngMode == 2
+                            ? radianceFp(scene, rng, origin, direction, 0, params, counters)
+                            : radiance(scene, rng, pixel, 0, origin, direction, 0, params, counters);
       if (selected) {
         colours[3 * pixel + 0] = colour.x;
         colours[3 * pixel + 1] = colour.y;

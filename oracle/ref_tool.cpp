@@ -14,6 +14,8 @@
 // reference's own dod::Scene::render for bench.py --impl reference.
 // ============================================================================================
 #include "dod/Scene.h"
+#include "fp/Render.h"
+#include "fp/SceneBuilder.h"
 #include "math/Camera.h"
 #include "math/Vec3.h"
 #include "util/ArrayOutput.h"
@@ -197,7 +199,9 @@ int usage() {
                "ref_tool check-recipes\n"
                "ref_tool pass NAME W H SEED PASS NU NV MAXDEPTH PREVIEW OUT.f64\n"
                "ref_tool render NAME W H SPP MAXCPUS SEED NU NV MAXDEPTH OUT.raw|-\n"
-               "ref_tool intersect NAME|FILE.ptscene WHICH NEARER RAYS.f64 OUT.f64\n";
+               "ref_tool intersect NAME|FILE.ptscene WHICH NEARER RAYS.f64 OUT.f64\n"
+               "ref_tool fp-pass NAME W H SEED NU NV MAXDEPTH PREVIEW OUT.f64   (fp::render, one pass)\n"
+               "ref_tool fp-render NAME W H SPP MAXCPUS SEED NU NV MAXDEPTH OUT.raw|-\n";
   return 2;
 }
 
@@ -318,6 +322,58 @@ int main(int argc, char **argv) {
       std::streambuf *saved = std::cout.rdbuf(std::cerr.rdbuf()); // Progressifier prints to cout
       const auto t0 = std::chrono::steady_clock::now();
       ArrayOutput output = scene.render(cam, p, [](ArrayOutput &) {}); // the unmodified entry point
+      const auto t1 = std::chrono::steady_clock::now();
+      std::cout.rdbuf(saved);
+      const std::string outPath = argv[11];
+      if (outPath != "-")
+        output.save(absolutePath(outPath));
+      std::printf("{\"seconds\": %.6f, \"total_samples\": %zu, \"pixels\": %d}\n",
+                  std::chrono::duration<double>(t1 - t0).count(), output.totalSamples(),
+                  p.width * p.height);
+      return 0;
+    }
+    if (cmd == "fp-pass" && argc == 11) {
+      // One whole-screen pass of the `fp` way (src/fp/Render.cpp:120-135) through its public
+      // entry point: samplesPerPixel = 1, maxCpus = 1 runs renderWholeScreen(seed) exactly once.
+      RenderParams p = sized(std::atoi(argv[3]), std::atoi(argv[4]));
+      p.seed = std::atoi(argv[5]);
+      p.firstBounceUSamples = std::atoi(argv[6]);
+      p.firstBounceVSamples = std::atoi(argv[7]);
+      p.maxDepth = std::atoi(argv[8]);
+      p.preview = std::atoi(argv[9]) != 0;
+      p.samplesPerPixel = 1;
+      p.maxCpus = 1;
+      fp::SceneBuilder builder;
+      Camera cam = makeScene(argv[2], builder, p.width, p.height);
+      std::streambuf *saved = std::cout.rdbuf(std::cerr.rdbuf());
+      ArrayOutput output = fp::render(cam, builder.scene(), p, [](const ArrayOutput &) {});
+      std::cout.rdbuf(saved);
+      std::vector<double> colours(static_cast<size_t>(p.width) * p.height * 3);
+      for (int y = 0; y < p.height; ++y)
+        for (int x = 0; x < p.width; ++x) {
+          const Vec3 c = output.rawPixelAt(x, y); // sum * (1/1)
+          double *dst = &colours[3 * (static_cast<size_t>(x) + static_cast<size_t>(y) * p.width)];
+          dst[0] = c.x();
+          dst[1] = c.y();
+          dst[2] = c.z();
+        }
+      std::ofstream out(absolutePath(argv[10]), std::ios::binary);
+      out.write(reinterpret_cast<const char *>(colours.data()), colours.size() * 8);
+      return 0;
+    }
+    if (cmd == "fp-render" && argc == 12) {
+      RenderParams p = sized(std::atoi(argv[3]), std::atoi(argv[4]));
+      p.samplesPerPixel = std::atoi(argv[5]);
+      p.maxCpus = std::atoi(argv[6]);
+      p.seed = std::atoi(argv[7]);
+      p.firstBounceUSamples = std::atoi(argv[8]);
+      p.firstBounceVSamples = std::atoi(argv[9]);
+      p.maxDepth = std::atoi(argv[10]);
+      fp::SceneBuilder builder;
+      Camera cam = makeScene(argv[2], builder, p.width, p.height);
+      std::streambuf *saved = std::cout.rdbuf(std::cerr.rdbuf());
+      const auto t0 = std::chrono::steady_clock::now();
+      ArrayOutput output = fp::render(cam, builder.scene(), p, [](const ArrayOutput &) {});
       const auto t1 = std::chrono::steady_clock::now();
       std::cout.rdbuf(saved);
       const std::string outPath = argv[11];
