@@ -94,6 +94,11 @@ typedef struct PtRenderParams {
 #define PTB200_RNG_KEYED_PHILOX 0        /* counter-based, parallel over pixels: throughput mode */
 #define PTB200_RNG_MT19937_SEQUENTIAL 1  /* the reference's own stream (Scene.cpp:211-216): one
                                             mt19937(seed+s) per pass walked row-major */
+#define PTB200_RNG_MT19937_PER_PIXEL 2   /* the reference's `fp` way (`--way fp`, src/fp/Render.cpp:
+                                            76-135): pass s seeds one mt19937(H*W*(seed+s) + x*W + y)
+                                            per pixel, strata are walked v-major and the emission is
+                                            added after the average.  Exact AND parallel over pixels;
+                                            the image is fp::render's with --max-cpus 1 */
 
 /* What a backend-specific caller may set beyond RenderParams.  Zero-initialise for defaults. */
 typedef struct PtRenderOptions {

@@ -91,6 +91,9 @@ __device__ __forceinline__ void sweepSpheres(const double4 *__restrict__ spheres
 }
 
 // ---- one ray against one triangle, the reference's Moller-Trumbore (Scene.cpp:62-98) -------
+// kFpWay: fp::Triangle::intersect (src/fp/Triangle.cpp:9-41) is the same arithmetic but rejects
+// `t < Epsilon` where Scene.cpp:94 accepts `t > Epsilon`, i.e. t == Epsilon is a hit there.
+template <bool kFpWay = false>
 __device__ __forceinline__ void testTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 d, int index,
                                              Nearest &best) {
   const V3 pVec = cross(d, e2);
@@ -103,7 +106,7 @@ __device__ __forceinline__ void testTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 d, in
   const double t = dot(e2, qVec) * invDet;
   // `continue` conditions of Scene.cpp:67,89 and the acceptance test of :94, as one predicate.
   const bool reject = (fabs(det) < kEpsilon) | (u < 0.0) | (u > 1.0) | (v < 0.0) | (u + v > 1);
-  const bool accept = !reject & (t > kEpsilon) & (t < best.t);
+  const bool accept = !reject & (kFpWay ? t >= kEpsilon : t > kEpsilon) & (t < best.t);
   if (accept) {
     best.t = t;
     best.det = det;
@@ -114,6 +117,7 @@ __device__ __forceinline__ void testTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 d, in
 // Sweeps triangles [0, count) of a tile that sits in shared memory; `count` is even.
 // Every lane of a warp reads the same addresses (broadcast); two triangles per iteration so
 // each of the 9 arrays is read with one 16-byte load.
+template <bool kFpWay = false>
 __device__ __forceinline__ void sweepTile(const double *__restrict__ tile, int tileTris, int count,
                                           int firstIndex, V3 o, V3 d, Nearest &best) {
 #pragma unroll 1
@@ -127,10 +131,10 @@ __device__ __forceinline__ void sweepTile(const double *__restrict__ tile, int t
     const double2 e2x = *reinterpret_cast<const double2 *>(tile + 6 * tileTris + i);
     const double2 e2y = *reinterpret_cast<const double2 *>(tile + 7 * tileTris + i);
     const double2 e2z = *reinterpret_cast<const double2 *>(tile + 8 * tileTris + i);
-    testTriangle(mk(v0x.x, v0y.x, v0z.x), mk(e1x.x, e1y.x, e1z.x), mk(e2x.x, e2y.x, e2z.x), o, d,
-                 firstIndex + i, best);
-    testTriangle(mk(v0x.y, v0y.y, v0z.y), mk(e1x.y, e1y.y, e1z.y), mk(e2x.y, e2y.y, e2z.y), o, d,
-                 firstIndex + i + 1, best);
+    testTriangle<kFpWay>(mk(v0x.x, v0y.x, v0z.x), mk(e1x.x, e1y.x, e1z.x), mk(e2x.x, e2y.x, e2z.x), o, d,
+                         firstIndex + i, best);
+    testTriangle<kFpWay>(mk(v0x.y, v0y.y, v0z.y), mk(e1x.y, e1y.y, e1z.y), mk(e2x.y, e2y.y, e2z.y), o, d,
+                         firstIndex + i + 1, best);
   }
 }
 
@@ -171,6 +175,7 @@ __device__ __forceinline__ bool prefilterTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 
   return !(detTooSmall | xNegative | yNegative) & (xs + ys <= hi);
 }
 
+template <bool kFpWay = false>
 __device__ __forceinline__ void sweepTilePrefiltered(const double *__restrict__ tile, int tileTris,
                                                      int count, int firstIndex, V3 o, V3 d,
                                                      Nearest &best) {
@@ -199,10 +204,10 @@ __device__ __forceinline__ void sweepTilePrefiltered(const double *__restrict__ 
     while (survivors) { // ascending index: the serial loop's tie-break order
       const int i = chunk + __ffsll(static_cast<long long>(survivors)) - 1;
       survivors &= survivors - 1;
-      testTriangle(mk(tile[0 * tileTris + i], tile[1 * tileTris + i], tile[2 * tileTris + i]),
-                   mk(tile[3 * tileTris + i], tile[4 * tileTris + i], tile[5 * tileTris + i]),
-                   mk(tile[6 * tileTris + i], tile[7 * tileTris + i], tile[8 * tileTris + i]), o, d,
-                   firstIndex + i, best);
+      testTriangle<kFpWay>(mk(tile[0 * tileTris + i], tile[1 * tileTris + i], tile[2 * tileTris + i]),
+                           mk(tile[3 * tileTris + i], tile[4 * tileTris + i], tile[5 * tileTris + i]),
+                           mk(tile[6 * tileTris + i], tile[7 * tileTris + i], tile[8 * tileTris + i]), o, d,
+                           firstIndex + i, best);
     }
   }
 }
@@ -291,7 +296,7 @@ __device__ __forceinline__ unsigned stage0Keep2(float2 v0x, float2 v0y, float2 v
 // immediate offsets address all fourteen 16-byte loads; `exact` is the tile's first record in the
 // AoS FP64 array (10 doubles per triangle, global memory / L1).  count is a multiple of 4.
 constexpr int kFilterFloats = 14;
-template <bool kPacked, bool kRejectNegativeT>
+template <bool kPacked, bool kRejectNegativeT, bool kFpWay = false>
 __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter,
                                                 const double *__restrict__ exact, int tileTris,
                                                 int count, int firstIndex, V3 o, V3 d,
@@ -337,7 +342,7 @@ __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter
       const double2 *record = reinterpret_cast<const double2 *>(exact + 10 * static_cast<size_t>(i));
       const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
                     a4 = __ldg(record + 4);
-      testTriangle(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d, firstIndex + i, best);
+      testTriangle<kFpWay>(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d, firstIndex + i, best);
     }
   }
 }
@@ -453,6 +458,21 @@ __device__ __forceinline__ V3 shadeTerm(const MaterialView &mat, bool specular, 
     return add(e, incoming);
   const V3 k = mat.diffuse();
   return mk(fma(k.x, incoming.x, e.x), fma(k.y, incoming.y, e.y), fma(k.z, incoming.z, e.z));
+}
+
+// The `fp` way adds the emission after averaging (src/fp/Render.cpp:118), so a 1x1 level is
+// emission + (0 + term) * (1/1) with term = radiance(child) or diffuse * radiance(child)
+// (:66-73): the product is rounded on its own, unlike shadeTerm()'s.
+__device__ __forceinline__ V3 fpSubSampleTerm(const MaterialView &mat, bool specular, V3 incoming) {
+  if (specular)
+    return incoming;
+  const V3 k = mat.diffuse();
+  return mk(k.x * incoming.x, k.y * incoming.y, k.z * incoming.z);
+}
+__device__ __forceinline__ V3 fpLevelRadiance(const MaterialView &mat, V3 incomingLight, double reciprocal) {
+  const V3 e = mat.emission();
+  return mk(fma(incomingLight.x, reciprocal, e.x), fma(incomingLight.y, reciprocal, e.y),
+            fma(incomingLight.z, reciprocal, e.z));
 }
 
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UBLKCP, SYNCS) ----------------------------

@@ -2,7 +2,9 @@
 //
 //   renderKeyedKernel       persistent megakernel, one path per LANE, keyed Philox RNG
 //                           (throughput mode; replaces the pass/pixel loops of
-//                           dod::Scene::render + radiance + intersect, Scene.cpp:115-254)
+//                           dod::Scene::render + radiance + intersect, Scene.cpp:115-254);
+//                           its kWay = 1 instantiation renders the reference's `fp` way instead:
+//                           one mt19937 per (pass, pixel), src/fp/Render.cpp:76-135
 //   renderSequentialKernel  one pass per WARP, the reference's own mt19937 stream walked in
 //                           row-major order (Scene.cpp:208-220), primitives spread over lanes
 //   reducePassesKernel      per-pixel accumulation of per-pass samples IN PASS ORDER
@@ -15,6 +17,7 @@
 #include "pt_kernels.h"
 
 #include "pt_device.cuh"
+#include "pt_mt19937.cuh"
 
 #include <cstdlib>
 
@@ -49,11 +52,13 @@ __host__ __device__ inline uint32_t smemAfterTiles(uint32_t numSpheres, uint32_t
 // consecutive banks; that keeps ~32 registers per thread free for a third resident CTA.
 constexpr uint32_t kPrimaryDoubles = 16;
 constexpr uint32_t kPendingDoubles = 8;   // the prefetched next sample, see the megakernel
+constexpr uint32_t kPendingDoublesFp = 9; //   ... plus its engine's two running seed words
 constexpr int kPrefetchBatch = 12;        // refill the prefetch slots when this many lanes' are empty
 __host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
-                               uint32_t threadsForPrimarySlots) {
+                               uint32_t threadsForPrimarySlots, int way) {
   return smemAfterTiles(numSpheres, tileTris, numTiles, sweep) +
-         static_cast<size_t>(threadsForPrimarySlots) * (kPrimaryDoubles + kPendingDoubles) * sizeof(double);
+         static_cast<size_t>(threadsForPrimarySlots) *
+             (kPrimaryDoubles + (way == 1 ? kPendingDoublesFp : kPendingDoubles)) * sizeof(double);
 }
 
 // Streams tiles cyclically (0,1,..,n-1,0,1,..) through two buffers with TMA bulk copies.
@@ -121,18 +126,18 @@ __device__ __forceinline__ TileStream makeTileStream(unsigned char *smemBase, co
 }
 
 // One tile of the sweep, whichever variant: `tile` is what the TileStream staged.
-template <int kSweep>
+template <int kSweep, bool kFpWay = false>
 __device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const unsigned char *tile,
                                                 uint32_t tileIndex, V3 o, V3 d, Nearest &best) {
   const int tileTris = static_cast<int>(scene.tileTris);
   const int first = static_cast<int>(tileIndex * scene.tileTris);
   if (kSweep >= 2)
-    sweepTileStage0<kSweep >= 3, kSweep == 4>(reinterpret_cast<const float *>(tile),
+    sweepTileStage0<kSweep >= 3, kSweep == 4, kFpWay>(reinterpret_cast<const float *>(tile),
                     scene.triExact + static_cast<size_t>(first) * 10, tileTris, tileTris, first, o, d, best);
   else if (kSweep == 1)
-    sweepTilePrefiltered(reinterpret_cast<const double *>(tile), tileTris, tileTris, first, o, d, best);
+    sweepTilePrefiltered<kFpWay>(reinterpret_cast<const double *>(tile), tileTris, tileTris, first, o, d, best);
   else
-    sweepTile(reinterpret_cast<const double *>(tile), tileTris, tileTris, first, o, d, best);
+    sweepTile<kFpWay>(reinterpret_cast<const double *>(tile), tileTris, tileTris, first, o, d, best);
 }
 
 // =============================================================================================
@@ -170,6 +175,40 @@ static __device__ __noinline__ void keyedCameraRay(const DeviceCamera &camera, u
   cameraRay(camera, px, py, ux, uy, ua, ur, origin, direction);
 }
 
+// ---- the `fp` way: one std::mt19937 per (pass, pixel) ---------------------------------------
+// Engine seed of renderOnePixel (src/fp/Render.cpp:125-126): height*width*seed + x*width + y
+// (x*width, the reference's own indexing), evaluated in size_t and reduced mod 2^32 by
+// mersenne_twister_engine::seed — i.e. plain uint32 arithmetic.
+__device__ __forceinline__ uint32_t fpEngineSeed(uint32_t width, uint32_t height, int passSeed, int px, int py) {
+  return height * width * static_cast<uint32_t>(passSeed) + static_cast<uint32_t>(px) * width +
+         static_cast<uint32_t>(py);
+}
+__device__ __forceinline__ double fpCanonical(LaneMt19937 &rng, uint32_t *history) {
+  const uint32_t lo = rng.word<false>(history);
+  const uint32_t hi = rng.word<false>(history);
+  return canonicalFromWords(lo, hi);
+}
+// Seeds the engine of a prefetched sample and draws its camera ray (Camera::randomRay draws two
+// doubles, rayFromUnit two more only when the aperture is open, Camera.h:30-33,56-58).  Always
+// executed by a batch of lanes together (see the megakernel), so out of line.
+static __device__ __noinline__ void fpCameraRay(const DeviceCamera &camera, uint32_t engineSeed, int px, int py,
+                                         uint32_t *history, uint32_t &seedWordA, uint32_t &seedWordB,
+                                         V3 &origin, V3 &direction) {
+  LaneMt19937 rng;
+  rng.seed(engineSeed);
+  double u[4] = {0, 0, 0, 0};
+  const int draws = camera.apertureRadius == 0 ? 2 : 4;
+#pragma unroll 1
+  for (int i = 0; i < draws; ++i) {
+    const uint32_t lo = rng.word<true>(history);
+    const uint32_t hi = rng.word<true>(history);
+    u[i] = canonicalFromWords(lo, hi);
+  }
+  cameraRay(camera, px, py, u[0], u[1], u[2], u[3], origin, direction);
+  seedWordA = rng.a;
+  seedWordB = rng.b;
+}
+
 // A surface a bounce leaves from: what radiance() holds between its intersect() and its
 // sampling loop (Scene.cpp:135-152).
 struct Surface {
@@ -178,9 +217,10 @@ struct Surface {
   uint32_t material;
 };
 
-template <int kBlock, int kMinBlocks, int kSweep>
+template <int kBlock, int kMinBlocks, int kSweep, int kWay>
 __global__ void __launch_bounds__(kBlock, kMinBlocks)
     renderKeyedKernel(const __grid_constant__ KeyedArgs args) {
+  constexpr bool kFp = kWay == 1;
   extern __shared__ __align__(128) unsigned char smemRaw[];
   const DeviceScene &scene = args.scene;
   TileStream stream = makeTileStream(smemRaw, scene, kSweep);
@@ -219,6 +259,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   // levels 1.. of the current sub-path: material index and branch taken
   uint16_t stackMaterial[kMaxDepth];
   bool stackSpecular[kMaxDepth];
+  // fp way: this lane's engine, and the words it has generated (thread-local memory).
+  LaneMt19937 rng{0u, 0u, 0u};
+  uint32_t history[kFp ? kMtHistoryWords : 1];
+  const uint32_t cameraWords = args.camera.apertureRadius == 0 ? 4u : 8u;
 
   for (;;) {
     // ---- 1. tickets and camera rays, prefetched in batches ----
@@ -249,7 +293,14 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
             args.samples[3 * item + 2] = 0.0;
           } else {
             V3 o, d;
-            keyedCameraRay(args.camera, nextKey, nextPixel, px, py, o, d);
+            if (kFp) {
+              uint32_t seedWordA, seedWordB;
+              fpCameraRay(args.camera, fpEngineSeed(args.width, args.height, static_cast<int>(nextKey), px, py),
+                          px, py, history, seedWordA, seedWordB, o, d);
+              pendingSlot[8 * kBlock] = __hiloint2double(static_cast<int>(seedWordA), static_cast<int>(seedWordB));
+            } else {
+              keyedCameraRay(args.camera, nextKey, nextPixel, px, py, o, d);
+            }
             pendingSlot[0 * kBlock] = o.x;
             pendingSlot[1 * kBlock] = o.y;
             pendingSlot[2 * kBlock] = o.z;
@@ -274,6 +325,15 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         const double packed = pendingSlot[7 * kBlock];
         key0 = static_cast<uint32_t>(__double2hiint(packed));
         pixel = static_cast<uint32_t>(__double2loint(packed));
+        if (kFp) { // take over the prefetched engine: its camera words move to the front
+          const double words = pendingSlot[8 * kBlock];
+          rng.a = static_cast<uint32_t>(__double2hiint(words));
+          rng.b = static_cast<uint32_t>(__double2loint(words));
+          rng.k = cameraWords;
+#pragma unroll
+          for (uint32_t i = 0; i < kMtPrefetchWords; ++i)
+            history[i] = history[kMtWords + i];
+        }
         pendingValid = false;
         depth = 0;
         mode = kTracing;
@@ -299,7 +359,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     for (uint32_t j = 0; j < scene.numTiles; ++j) {
       const unsigned char *tile = resident ? stream.tile(0) : stream.acquire();
       if (tracing)
-        sweepStagedTile<kSweep>(scene, tile, j, origin, direction, best);
+        sweepStagedTile<kSweep, kFp>(scene, tile, j, origin, direction, best);
       if (!resident)
         stream.release();
     }
@@ -329,6 +389,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
           incoming = shadeTerm(materialOf(scene, hit.material), true, mk(0, 0, 0));
           ended = true;
           terminalPrimary = depth == 0;
+          if (kFp && depth > 0) { // ... and its (u, v, p) draws still advance the sample's engine
+#pragma unroll 1
+            for (int i = 0; i < 6; ++i)
+              rng.word<false>(history);
+          }
         } else {
           needSurface = true;
         }
@@ -365,24 +430,30 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       bool sampleDone = false;
       V3 colour = incoming;
       if (depth == 0) {
-        if (terminalPrimary) { // maxDepth == 1: numSub children, each Vec3()
+        if (terminalPrimary && !kFp) { // maxDepth == 1: numSub children, each Vec3()
           acc = mk(0, 0, 0);
 #pragma unroll 1
           for (int k = 0; k < numSub; ++k)
             acc = add(acc, incoming);
           colour = scale(acc, invNumSub);
-        }
+        } // fp way: emission + (sum of zero terms) / numSub, which `incoming` already is
         sampleDone = true; // camera ray missed / preview / maxDepth == 1
       } else {
         // unwind levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum), then the
         // primary hit's own term, in the reference's summation order
 #pragma unroll 1
-        for (int level = depth - 1; level >= 1; --level)
-          incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
-        acc = add(acc, shadeTerm(materialOf(scene, primaryMaterial), primarySpecular, incoming));
+        for (int level = depth - 1; level >= 1; --level) {
+          const MaterialView mat = materialOf(scene, stackMaterial[level]);
+          incoming = kFp ? fpLevelRadiance(mat, fpSubSampleTerm(mat, stackSpecular[level], incoming), 1.0)
+                         : shadeTerm(mat, stackSpecular[level], incoming);
+        }
+        const MaterialView primaryMat = materialOf(scene, primaryMaterial);
+        acc = add(acc, kFp ? fpSubSampleTerm(primaryMat, primarySpecular, incoming)
+                           : shadeTerm(primaryMat, primarySpecular, incoming));
         ++subPath;
         if (subPath >= numSub) {
-          colour = scale(acc, invNumSub); // Scene.cpp:178
+          colour = kFp ? fpLevelRadiance(primaryMat, acc, invNumSub) // src/fp/Render.cpp:118
+                       : scale(acc, invNumSub);                      // Scene.cpp:178
           sampleDone = true;
         } else {
           depth = 0;
@@ -411,12 +482,24 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         surface.material = primaryMaterial;
       }
       double ru, rv, rp;
-      KeyedDraws{key0}.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
+      if (kFp) { // toUVSample draws u then v, then p (src/fp/Render.cpp:97-102,116)
+        ru = rv = rp = 0;
+#pragma unroll 1
+        for (int i = 0; i < 3; ++i) { // one copy of the generator code: shift the draws through
+          const double drawn = fpCanonical(rng, history);
+          ru = rv;
+          rv = rp;
+          rp = drawn;
+        }
+      } else {
+        KeyedDraws{key0}.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
+      }
       double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
       if (fromPrimary) {
+        // Strata: u-major in Scene.cpp:155-156, v-major in the fp way (src/fp/Render.cpp:109-110).
         // x / n == x * (1/n) exactly when n is a power of two (the default 4x4 strata)
-        const double su = static_cast<double>(subPath / args.firstBounceV) + ru;
-        const double sv = static_cast<double>(subPath % args.firstBounceV) + rv;
+        const double su = static_cast<double>(kFp ? subPath % args.firstBounceU : subPath / args.firstBounceV) + ru;
+        const double sv = static_cast<double>(kFp ? subPath / args.firstBounceU : subPath % args.firstBounceV) + rv;
         u = args.firstBounceUPow2 ? su * args.invFirstBounceU : ieeeDiv(su, static_cast<double>(args.firstBounceU));
         v = args.firstBounceVPow2 ? sv * args.invFirstBounceV : ieeeDiv(sv, static_cast<double>(args.firstBounceV));
       }
@@ -976,10 +1059,10 @@ __global__ void fp64PeakKernel(double *sink, int iterations) {
 // =============================================================================================
 constexpr int kSequentialWarps = 2;
 
-template <int kBlock, int kMinBlocks, int kSweep>
+template <int kBlock, int kMinBlocks, int kSweep, int kWay = 0>
 cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t stream) {
-  auto kernel = renderKeyedKernel<kBlock, kMinBlocks, kSweep>;
-  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep, kBlock);
+  auto kernel = renderKeyedKernel<kBlock, kMinBlocks, kSweep, kWay>;
+  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep, kBlock, kWay);
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smemBytes));
   if (err != cudaSuccess)
@@ -1022,6 +1105,15 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
 }
 
 cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream) {
+  if (args.way == 1) { // the fp way: the default configurations and the unfiltered fallback only
+    switch (config) {
+    case 1: return launchKeyedConfig<256, 2, 1, 1>(args, numSms, stream);
+    case 3: return launchKeyedConfig<256, 2, 3, 1>(args, numSms, stream);
+    case 4: return launchKeyedConfig<256, 2, 4, 1>(args, numSms, stream);
+    case 24: return launchKeyedConfig<256, 3, 4, 1>(args, numSms, stream);
+    default: return cudaErrorInvalidValue;
+    }
+  }
   switch (config) {
   case 0: return launchKeyedConfig<256, 2, 0>(args, numSms, stream);
   case 1: return launchKeyedConfig<256, 2, 1>(args, numSms, stream);
@@ -1069,7 +1161,7 @@ cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream) {
 }
 
 cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream) {
-  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, args.sweep, 0);
+  const size_t smemBytes = keyedSmemBytes(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, args.sweep, 0, 0);
   cudaError_t err = cudaFuncSetAttribute(intersectKernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smemBytes));
   if (err != cudaSuccess)

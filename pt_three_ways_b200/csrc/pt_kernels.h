@@ -24,7 +24,8 @@ struct PtHitDevice { // == PtHit (include/ptb200.h)
 struct KeyedArgs {
   DeviceScene scene;
   DeviceCamera camera;
-  uint32_t width;
+  uint32_t width, height;
+  int32_t way;                     // 0: dod estimator + keyed Philox; 1: the `fp` way, mt19937 per (pass, pixel)
   int32_t rowBegin, rowStep;
   uint32_t ownPixels;              // pixels of the selected rows
   unsigned long long totalItems;   // ownPixels * passes of this batch
@@ -84,7 +85,7 @@ struct IntersectArgs {
 };
 
 size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
-                      uint32_t threadsForPrimarySlots);
+                      uint32_t threadsForPrimarySlots, int way);
 int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable); // 10 * launchShape + sweepVariant
 cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream);
 cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream);

@@ -1,0 +1,90 @@
+// std::mt19937 for ONE LANE, for the reference's `fp` way, which seeds a fresh engine per
+// (pass, pixel) (src/fp/Render.cpp:125-126) and then draws at most a few hundred words from it.
+//
+// A textbook engine needs 624 words of state per lane, written once by the seeding recurrence and
+// twisted in place.  A sample of the default configuration draws <= 488 words, all of the first
+// generation, and word k of that generation depends on three SEED words only:
+//     new[k] = (k < 227 ? seed[k+397] : new[k-227]) ^ twist(seed[k], seed[k+1])
+// The seed words come from a first-order recurrence (x[i] = 1812433253*(x[i-1]^(x[i-1]>>30)) + i),
+// so the engine keeps two running copies of it in registers — `a` = seed[k] and `b` = seed[k+397]
+// (397 steps ahead, paid once per sample) — and only the words it has GENERATED go to the lane's
+// history array (thread-local memory; read back 227 draws later, and by later generations).
+// From word 624 on it is the textbook in-place algorithm on that array.
+//
+// Compiled by nvcc for the kernels and by g++ for tests/host unit test (PT_HD empty).
+#pragma once
+
+#include <cstdint>
+
+#ifdef __CUDACC__
+#define PT_HD __host__ __device__ __forceinline__
+#else
+#define PT_HD inline
+#endif
+
+namespace ptb200 {
+
+constexpr uint32_t kMtWords = 624;
+constexpr uint32_t kMtShift = 397;
+// The history array has 8 extra words: the first words of the PREFETCHED next sample (its
+// camera-ray draws) wait there while the current sample still owns [0, 624).
+constexpr uint32_t kMtPrefetchWords = 8;
+constexpr uint32_t kMtHistoryWords = kMtWords + kMtPrefetchWords;
+
+struct LaneMt19937 {
+  uint32_t a; // seed[k]      (meaningful while k < 624)
+  uint32_t b; // seed[k+397]  (meaningful while k < 227)
+  uint32_t k; // words drawn so far
+
+  static PT_HD uint32_t lcg(uint32_t x, uint32_t i) { return 1812433253u * (x ^ (x >> 30)) + i; }
+  static PT_HD uint32_t twist(uint32_t upper, uint32_t lower) {
+    const uint32_t y = (upper & 0x80000000u) | (lower & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  }
+  static PT_HD uint32_t temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+
+  PT_HD void seed(uint32_t value) { // mersenne_twister_engine::seed(value), lazily
+    a = value;
+    uint32_t x = value;
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (uint32_t i = 1; i <= kMtShift; ++i)
+      x = lcg(x, i);
+    b = x;
+    k = 0;
+  }
+
+  // Next 32-bit output.  `store` is where generated word k is kept: history + k, except for the
+  // prefetched camera draws (history + 624 + k, moved to the front when the sample starts).
+  template <bool kPrefetch>
+  PT_HD uint32_t word(uint32_t *history) {
+    const uint32_t j = k % kMtWords;
+    uint32_t w;
+    if (k < kMtWords) {
+      const uint32_t next = k + 1 < kMtWords ? lcg(a, k + 1) : history[0]; // word 623 pairs with NEW word 0
+      uint32_t source;
+      if (k < kMtWords - kMtShift) {
+        source = b;
+        b = lcg(b, k + kMtShift + 1); // runs past seed[623] at k == 226; never read after that
+      } else {
+        source = history[k - (kMtWords - kMtShift)];
+      }
+      w = source ^ twist(a, next);
+      a = next;
+    } else { // later generations: in place, as the serial algorithm does it
+      w = history[(j + kMtShift) % kMtWords] ^ twist(history[j], history[(j + 1) % kMtWords]);
+    }
+    history[kPrefetch ? kMtWords + j : j] = w;
+    ++k;
+    return temper(w);
+  }
+};
+
+} // namespace ptb200

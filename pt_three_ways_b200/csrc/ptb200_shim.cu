@@ -183,7 +183,8 @@ int validateParams(const PtRenderParams *p, const PtRenderOptions *o) {
   if (p->firstBounceUSamples <= 0 || p->firstBounceVSamples <= 0)
     return fail(PTB200_EINVAL, "first-bounce sample counts must be positive");
   if (o) {
-    if (o->rngMode != PTB200_RNG_KEYED_PHILOX && o->rngMode != PTB200_RNG_MT19937_SEQUENTIAL)
+    if (o->rngMode != PTB200_RNG_KEYED_PHILOX && o->rngMode != PTB200_RNG_MT19937_SEQUENTIAL &&
+        o->rngMode != PTB200_RNG_MT19937_PER_PIXEL)
       return fail(PTB200_EINVAL, "unknown rngMode %d", o->rngMode);
     if (o->rowStep < 0 || o->rowBegin < 0)
       return fail(PTB200_EINVAL, "negative row partition");
@@ -436,7 +437,12 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
     passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(opt.passesPerBatch));
   passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses));
   PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
-  const int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable);
+  const bool fpWay = opt.rngMode == PTB200_RNG_MT19937_PER_PIXEL;
+  int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable);
+  if (fpWay) { // instantiated for the default configurations and the FP64 fallback only
+    const int sweep = keyedConfig % 10;
+    keyedConfig = sweep <= 1 ? 1 : sweep == 4 ? (keyedConfig / 10 == 2 ? 24 : 4) : 3;
+  }
   if (!sequential && keyedConfig % 10 >= 2) {
     if (!ctx->filterUsable)
       return fail(PTB200_EINVAL, "scene coordinates exceed the range the FP32 stage-0 sweep supports; "
@@ -479,6 +485,8 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.scene = ctx->scene;
       a.camera = toDeviceCamera(*camera);
       a.width = static_cast<uint32_t>(params->width);
+      a.height = static_cast<uint32_t>(params->height);
+      a.way = fpWay ? 1 : 0;
       a.rowBegin = rowBegin;
       a.rowStep = rowStep;
       a.ownPixels = ownPixels;

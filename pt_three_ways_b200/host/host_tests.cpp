@@ -12,6 +12,7 @@
 #include "PngWriter.h"
 #include "Scene.h"
 #include "SceneRecipes.h"
+#include "../csrc/pt_mt19937.cuh" // the per-lane engine of the fp way, host-compiled
 
 #include <cmath>
 #include <cstdio>
@@ -19,6 +20,7 @@
 #include <fstream>
 #include <iostream>
 #include <limits>
+#include <random>
 #include <sstream>
 #include <unistd.h>
 
@@ -411,6 +413,38 @@ static void recipeTests(const std::string &scenesDir, const std::string &fixture
   }
 }
 
+// The lazily seeded per-lane mt19937 of the `fp` way (csrc/pt_mt19937.cuh) against
+// std::mt19937: first generation from the two running seed words, the prefetch hand-over of
+// the camera draws, and the in-place later generations.
+static void laneMt19937Tests() {
+  for (uint32_t seed : {0u, 1u, 5489u, 0xffffffffu, 123456789u, 640u * 480u * 7u + 17u}) {
+    for (uint32_t cameraWords : {4u, 8u}) {
+      std::mt19937 reference(seed);
+      LaneMt19937 rng;
+      uint32_t history[kMtHistoryWords];
+      for (uint32_t &word : history)
+        word = 0xdeadbeefu;
+      rng.seed(seed);
+      int bad = 0;
+      for (uint32_t i = 0; i < cameraWords; ++i)
+        bad += rng.word<true>(history) != reference();
+      for (uint32_t i = 0; i < kMtPrefetchWords; ++i) // what the megakernel does when the sample starts
+        history[i] = history[kMtWords + i];
+      for (int i = 0; i < 3000; ++i)
+        bad += rng.word<false>(history) != reference();
+      CHECK(bad == 0);
+    }
+  }
+  std::mt19937 defaultSeeded; // the standard's own known answer: 10000th output = 4123659995
+  LaneMt19937 rng;
+  uint32_t history[kMtHistoryWords];
+  rng.seed(5489u);
+  uint32_t last = 0;
+  for (int i = 0; i < 10000; ++i)
+    last = rng.word<false>(history);
+  CHECK(last == 4123659995u);
+}
+
 int main(int argc, char **argv) {
   std::string scenesDir = "/root/reference/scenes", fixtureDir = "tests/golden/scenes";
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -424,6 +458,7 @@ int main(int argc, char **argv) {
   mathTests();
   sceneAdaptorTests();
   pngWriterTests();
+  laneMt19937Tests();
   int32_t deviceCount = 0;
   ptb200_device_count(&deviceCount);
   if (deviceCount > 0)

@@ -10,6 +10,8 @@ Outputs (all small, committed):
   pass_<case>.npy           per-pass images from the reference's radiance()/randomRay()
   hits_<scene>.npz          rays + the reference's Scene::intersect records
   render_asis_cornell.raw   what the unmodified dod::Scene::render returns (raw format)
+  fp_pass_<case>.npy        one whole-screen pass of the reference's `fp` way (fp::render, spp 1)
+  fp_render_cornell.raw     the unmodified fp::render, 16x16, 5 spp, --max-cpus 1, seed 3
 """
 import json
 import os
@@ -40,6 +42,21 @@ PASS_CASES = [
     ("multi-sphere_24x18_s5_p0", "multi-sphere", 24, 18, 5, 0, 4, 4, 5, 0),
     ("example1_24x18_s6_p0", "example1", 24, 18, 6, 0, 4, 4, 5, 0),
     ("bbc-owl_24x18_s8_p0", "bbc-owl", 24, 18, 8, 0, 4, 4, 5, 0),
+]
+# (case name, scene, width, height, seed, firstU, firstV, maxDepth, preview): src/fp/Render.cpp
+FP_PASS_CASES = [
+    ("cornell_32x24_s1", "cornell", 32, 24, 1, 4, 4, 5, 0),
+    ("cornell_32x24_s2", "cornell", 32, 24, 2, 4, 4, 5, 0),
+    ("cornell_20x20_s7_u2v3_d3", "cornell", 20, 20, 7, 2, 3, 3, 0),
+    ("cornell_12x9_s5_u8v8_d6", "cornell", 12, 9, 5, 8, 8, 6, 0),   # > 624 words per engine
+    ("cornell_16x12_s3_d1", "cornell", 16, 12, 3, 4, 4, 1, 0),
+    ("cornell_16x12_s3_preview", "cornell", 16, 12, 3, 4, 4, 5, 1),
+    ("suzanne_24x18_s2", "suzanne", 24, 18, 2, 4, 4, 5, 0),
+    ("ce_8x6_s1", "ce", 8, 6, 1, 4, 4, 5, 0),
+    ("single-sphere_24x18_s4", "single-sphere", 24, 18, 4, 4, 4, 5, 0),
+    ("multi-sphere_24x18_s5", "multi-sphere", 24, 18, 5, 4, 4, 5, 0),
+    ("example1_24x18_s6", "example1", 24, 18, 6, 4, 4, 5, 0),
+    ("bbc-owl_24x18_s8", "bbc-owl", 24, 18, 8, 4, 4, 5, 0),
 ]
 CAMERA_SIZES = [(64, 48), (640, 480), (1280, 720), (1920, 1080), (256, 256), (16, 16)]
 
@@ -95,6 +112,12 @@ def main():
         # --max-cpus 1, seed 1) but in the raw format.
         out = os.path.join(GOLDEN, "render_asis_cornell.raw")
         print(ob.ref_render("cornell", 16, 16, 16, 1, 1, out))
+        # The `fp` way, through its unmodified entry point fp::render.
+        for case, scene, w, h, seed, fu, fv, depth, preview in FP_PASS_CASES:
+            img = ob.ref_fp_pass(scene, w, h, seed, tmp, fu, fv, depth, preview)
+            np.save(os.path.join(GOLDEN, f"fp_pass_{case}.npy"), img)
+            print("fp", case, float(img.min()), float(img.max()))
+        print(ob.ref_fp_render("cornell", 16, 16, 5, 1, 3, os.path.join(GOLDEN, "fp_render_cornell.raw")))
 
 
 if __name__ == "__main__":

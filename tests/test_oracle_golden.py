@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.golden.make_golden import PASS_CASES, SCENES
+from tests.golden.make_golden import FP_PASS_CASES, PASS_CASES, SCENES
 
 
 def load_npy(golden_dir, name):
@@ -44,6 +44,47 @@ def test_unmodified_render_is_sum_of_first_passes(scenes, oracle, golden_dir):
                                            oracle.RNG_MT19937_SEQUENTIAL)
     assert np.array_equal(got["counts"], counts.astype(np.uint64))
     assert np.abs(got["sums"] - sums).max() <= 1e-11  # 15 passes of values <= ~20
+
+
+# ---- the reference's `fp` way (src/fp/Render.cpp): mt19937 per (pass, pixel) -------------------
+@pytest.mark.parametrize("case", FP_PASS_CASES, ids=lambda c: c[0])
+def test_fp_way_pass_image_matches_reference(case, scenes, oracle, golden_dir):
+    """Golden: fp::render(spp=1, maxCpus=1) of the reference built from its own sources."""
+    name, scene_name, w, h, seed, fu, fv, depth, preview = case
+    want = load_npy(golden_dir, f"fp_pass_{name}.npy")
+    scene = scenes[scene_name]
+    params = oracle.params_array(w, h, spp=1, seed=seed, max_depth=depth, first_u=fu, first_v=fv, preview=preview)
+    got = oracle.OracleScene(scene).render(scene.camera(w, h), params, oracle.RNG_FP_PER_PIXEL, num_passes=1,
+                                           per_pass=True)["per_pass"][0]
+    assert np.abs(got - want).max() <= 1e-12  # measured: exactly 0
+
+
+def test_fp_way_unmodified_render_is_the_sum_of_its_passes(scenes, oracle, golden_dir):
+    """fp::render keeps every pass (no dropped tail, src/fp/Render.cpp:146-164); with --max-cpus 1
+    pass s uses seed + s and the passes are added in order."""
+    sums, counts = oracle.read_raw(os.path.join(golden_dir, "fp_render_cornell.raw"))
+    assert (counts == 5).all()
+    scene = scenes["cornell"]
+    got = oracle.OracleScene(scene).render(scene.camera(16, 16), oracle.params_array(16, 16, spp=5, seed=3),
+                                           oracle.RNG_FP_PER_PIXEL)
+    assert np.array_equal(got["counts"], counts.astype(np.uint64))
+    assert np.abs(got["sums"] - sums).max() <= 1e-11
+
+
+def test_fp_way_engine_seed_uses_the_reference_indexing(scenes, oracle):
+    """x*width + y (not y*width + x): pixels (x, y) and (y', x') with x*W + y == x'*W + y' share an
+    engine within a pass, e.g. (0, 1) and ... none inside a W x H frame with H <= W; but pass s+1
+    starts H*W further on, so (x, y, s) and (x - H, y, s + 1) collide when W > H: same engine, but
+    a different pixel position, hence a different camera ray.  Here: the colours differ, and the
+    whole image differs from the dod way's."""
+    scene = scenes["cornell"]
+    w, h = 16, 8
+    cam = scene.camera(w, h)
+    osc = oracle.OracleScene(scene)
+    fp = osc.render(cam, oracle.params_array(w, h, spp=2, seed=1), oracle.RNG_FP_PER_PIXEL, per_pass=True)
+    dod = osc.render(cam, oracle.params_array(w, h, spp=2, seed=1), oracle.RNG_MT19937_SEQUENTIAL, per_pass=True)
+    assert not np.array_equal(fp["per_pass"][0], dod["per_pass"][0])
+    assert fp["casts"] > 0 and abs(fp["casts"] / dod["casts"] - 1) < 0.2
 
 
 # ---- intersection records --------------------------------------------------------------------
