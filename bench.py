@@ -361,6 +361,17 @@ def run_ours(args):
                 "parity": "bit-exact vs the oracle's sequential policy, which equals the reference's "
                           "per-pass images (tests/test_oracle_golden.py)",
                 "note": "parallel over passes only (SURVEY.md section 0 item 3); not the timed headline"}
+            # ... and the reference's `fp` way (mt19937 per pass and pixel): exact AND parallel
+            # over pixels, so it runs in the megakernel on the full workload.
+            fst = ctx.render(camera, capi.make_params(WIDTH, HEIGHT, spp=SPP, seed=SEED),
+                             capi.make_options(rng_mode=capi.RNG_MT19937_PER_PIXEL, device=local_rank))
+            line["fp_way_mode"] = {
+                "value": fst["samples"] / fst["kernel_ms"] / 1e3, "unit": UNIT,
+                "sample": f"{SCENE} {WIDTH}x{HEIGHT}, {SPP} passes, PTB200_RNG_MT19937_PER_PIXEL",
+                "casts_per_sample": fst["casts"] / fst["samples"],
+                "parity": "bit-exact vs the oracle's fp policy, which equals fp::render of the reference "
+                          "(src/fp/Render.cpp) image for image (tests/golden/fp_pass_*.npy)",
+                "note": "the reference's --way fp semantics; not the timed headline"}
             threads = os.cpu_count() or 1
             v, info = cpu_reference_step(threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, **info,
