@@ -183,9 +183,9 @@ __device__ __forceinline__ uint32_t fpEngineSeed(uint32_t width, uint32_t height
   return height * width * static_cast<uint32_t>(passSeed) + static_cast<uint32_t>(px) * width +
          static_cast<uint32_t>(py);
 }
-__device__ __forceinline__ double fpCanonical(LaneMt19937 &rng, uint32_t *history) {
-  const uint32_t lo = rng.word<false>(history);
-  const uint32_t hi = rng.word<false>(history);
+__device__ __forceinline__ double fpCanonical(LaneMt19937 &rng, uint32_t *history, uint32_t storeLimit) {
+  const uint32_t lo = rng.word<false>(history, storeLimit);
+  const uint32_t hi = rng.word<false>(history, storeLimit);
   return canonicalFromWords(lo, hi);
 }
 // Seeds the engine of a prefetched sample and draws its camera ray (Camera::randomRay draws two
@@ -200,8 +200,8 @@ static __device__ __noinline__ void fpCameraRay(const DeviceCamera &camera, uint
   const int draws = camera.apertureRadius == 0 ? 2 : 4;
 #pragma unroll 1
   for (int i = 0; i < draws; ++i) {
-    const uint32_t lo = rng.word<true>(history);
-    const uint32_t hi = rng.word<true>(history);
+    const uint32_t lo = rng.word<true>(history, 0u);
+    const uint32_t hi = rng.word<true>(history, 0u);
     u[i] = canonicalFromWords(lo, hi);
   }
   cameraRay(camera, px, py, u[0], u[1], u[2], u[3], origin, direction);
@@ -259,10 +259,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   // levels 1.. of the current sub-path: material index and branch taken
   uint16_t stackMaterial[kMaxDepth];
   bool stackSpecular[kMaxDepth];
-  // fp way: this lane's engine, and the words it has generated (thread-local memory).
+  // fp way: this lane's engine, and the words it has generated (its slice of the scratch buffer).
   LaneMt19937 rng{0u, 0u, 0u};
-  uint32_t history[kFp ? kMtHistoryWords : 1];
+  uint32_t *const history =
+      kFp ? args.mtHistory + (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) * kMtHistoryStride : nullptr;
   const uint32_t cameraWords = args.camera.apertureRadius == 0 ? 4u : 8u;
+  const uint32_t storeLimit = args.mtStoreLimit;
 
   for (;;) {
     // ---- 1. tickets and camera rays, prefetched in batches ----
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
           if (kFp && depth > 0) { // ... and its (u, v, p) draws still advance the sample's engine
 #pragma unroll 1
             for (int i = 0; i < 6; ++i)
-              rng.word<false>(history);
+              rng.word<false>(history, storeLimit);
           }
         } else {
           needSurface = true;
@@ -486,7 +488,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         ru = rv = rp = 0;
 #pragma unroll 1
         for (int i = 0; i < 3; ++i) { // one copy of the generator code: shift the draws through
-          const double drawn = fpCanonical(rng, history);
+          const double drawn = fpCanonical(rng, history, storeLimit);
           ru = rv;
           rv = rp;
           rp = drawn;
@@ -1078,6 +1080,8 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
   unsigned long long grid = static_cast<unsigned long long>(numSms) * perSm;
   if (wanted < grid)
     grid = wanted ? wanted : 1;
+  if (kWay == 1 && (args.mtHistory == nullptr || grid * kBlock > args.mtHistoryThreads))
+    return cudaErrorInvalidValue; // scratch for the per-lane engines: see mtHistoryThreadsFor()
   kernel<<<static_cast<unsigned>(grid), kBlock, smemBytes, stream>>>(args);
   return cudaGetLastError();
 }
@@ -1103,6 +1107,9 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
   const int shape = small ? 2 : 0;
   return 10 * shape + sweep;
 }
+
+// Threads a persistent fp-way grid can have: its instantiations are 256 threads x <= 3 CTAs/SM.
+size_t mtHistoryThreadsFor(int numSms) { return static_cast<size_t>(numSms) * 768; }
 
 cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream) {
   if (args.way == 1) { // the fp way: the default configurations and the unfiltered fallback only

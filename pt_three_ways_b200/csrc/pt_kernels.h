@@ -34,6 +34,9 @@ struct KeyedArgs {
   int32_t firstBounceUPow2, firstBounceVPow2; // strata counts are powers of two:
   double invFirstBounceU, invFirstBounceV;    //   divide by multiplying with the exact reciprocal
   double *samples;                 // [passInBatch][ownPixel][3]
+  uint32_t *mtHistory;             // fp way: kMtHistoryStride words per thread of the grid (pt_mt19937.cuh)
+  size_t mtHistoryThreads;         //   ... how many threads it was sized for
+  uint32_t mtStoreLimit;           //   ... generated words >= this are never read back: not stored
   unsigned long long *ticket;      // work counter, zeroed before launch
   unsigned long long *castCounter;
 };
@@ -86,6 +89,7 @@ struct IntersectArgs {
 
 size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
                       uint32_t threadsForPrimarySlots, int way);
+size_t mtHistoryThreadsFor(int numSms);
 int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable); // 10 * launchShape + sweepVariant
 cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream);
 cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream);

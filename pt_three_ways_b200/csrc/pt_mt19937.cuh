@@ -8,8 +8,16 @@
 // The seed words come from a first-order recurrence (x[i] = 1812433253*(x[i-1]^(x[i-1]>>30)) + i),
 // so the engine keeps two running copies of it in registers — `a` = seed[k] and `b` = seed[k+397]
 // (397 steps ahead, paid once per sample) — and only the words it has GENERATED go to the lane's
-// history array (thread-local memory; read back 227 draws later, and by later generations).
-// From word 624 on it is the textbook in-place algorithm on that array.
+// history array (read back 227 draws later, and by later generations).  From word 624 on it is
+// the textbook in-place algorithm on that array.
+//
+// The history array is a per-thread CONTIGUOUS slice of a global scratch buffer, not thread-local
+// memory: local memory interleaves the lanes of a warp word by word, so lanes at different draw
+// counts dirty one 32-byte sector per 4-byte word (measured: 31 KB of DRAM traffic per sample,
+// 2.4 TB/s, long-scoreboard bound); a contiguous slice fills a sector with eight consecutive
+// draws of one lane and the touched prefix of all resident lanes (~1 KB each) stays in L2.
+// When a sample can draw at most `maxWords` <= 624 words, word k is read back only if
+// k + 227 < maxWords, so later words are not stored at all (`storeLimit`).
 //
 // Compiled by nvcc for the kernels and by g++ for tests/host unit test (PT_HD empty).
 #pragma once
@@ -30,6 +38,17 @@ constexpr uint32_t kMtShift = 397;
 // camera-ray draws) wait there while the current sample still owns [0, 624).
 constexpr uint32_t kMtPrefetchWords = 8;
 constexpr uint32_t kMtHistoryWords = kMtWords + kMtPrefetchWords;
+constexpr uint32_t kMtHistoryStride = 640; // words per thread in the scratch buffer (128-byte multiple)
+
+// Words [storeLimit, 624) of a sample's first generation are never read back.
+inline uint32_t mtStoreLimit(uint64_t maxWordsPerSample) {
+  if (maxWordsPerSample > kMtWords)
+    return 0xffffffffu;
+  const uint32_t readBack = maxWordsPerSample > kMtWords - kMtShift
+                                ? static_cast<uint32_t>(maxWordsPerSample) - (kMtWords - kMtShift)
+                                : 0u;
+  return readBack > kMtPrefetchWords ? readBack : kMtPrefetchWords;
+}
 
 struct LaneMt19937 {
   uint32_t a; // seed[k]      (meaningful while k < 624)
@@ -64,7 +83,7 @@ struct LaneMt19937 {
   // Next 32-bit output.  `store` is where generated word k is kept: history + k, except for the
   // prefetched camera draws (history + 624 + k, moved to the front when the sample starts).
   template <bool kPrefetch>
-  PT_HD uint32_t word(uint32_t *history) {
+  PT_HD uint32_t word(uint32_t *history, uint32_t storeLimit) {
     const uint32_t j = k % kMtWords;
     uint32_t w;
     if (k < kMtWords) {
@@ -81,7 +100,10 @@ struct LaneMt19937 {
     } else { // later generations: in place, as the serial algorithm does it
       w = history[(j + kMtShift) % kMtWords] ^ twist(history[j], history[(j + 1) % kMtWords]);
     }
-    history[kPrefetch ? kMtWords + j : j] = w;
+    if (kPrefetch)
+      history[kMtWords + j] = w;
+    else if (k < storeLimit)
+      history[j] = w;
     ++k;
     return temper(w);
   }

@@ -7,6 +7,7 @@
 #include "ptb200.h"
 
 #include "pt_kernels.h"
+#include "pt_mt19937.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -143,6 +144,7 @@ struct PtContext {
   bool filterUsable{false};    // FP32 stage 0 allowed (coordinates comfortably inside FP32 range)
   DeviceBuffer<PtPixelDevice> accumulator;
   DeviceBuffer<double> samples;
+  DeviceBuffer<uint32_t> mtHistory;          // fp way: scratch of the per-lane engines (pt_mt19937.cuh)
   DeviceBuffer<unsigned long long> counters; // [0] ticket, [1] casts
   int accWidth{0}, accHeight{0};
 };
@@ -443,6 +445,16 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
     const int sweep = keyedConfig % 10;
     keyedConfig = sweep <= 1 ? 1 : sweep == 4 ? (keyedConfig / 10 == 2 ? 24 : 4) : 3;
   }
+  size_t mtThreads = 0;
+  uint32_t mtLimit = 0;
+  if (fpWay) {
+    mtThreads = mtHistoryThreadsFor(ctx->numSms);
+    PT_CUDA(ctx->mtHistory.ensure(mtThreads * kMtHistoryStride));
+    // An engine draws the camera's words, then three doubles per stratum at depth 0 and per
+    // sub-path and level below it.
+    const uint64_t strata = static_cast<uint64_t>(params->firstBounceUSamples) * static_cast<uint64_t>(params->firstBounceVSamples);
+    mtLimit = mtStoreLimit(8u + 6u * strata * static_cast<uint64_t>(std::max(params->maxDepth, 0)));
+  }
   if (!sequential && keyedConfig % 10 >= 2) {
     if (!ctx->filterUsable)
       return fail(PTB200_EINVAL, "scene coordinates exceed the range the FP32 stage-0 sweep supports; "
@@ -502,6 +514,9 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.invFirstBounceU = 1.0 / static_cast<double>(a.firstBounceU);
       a.invFirstBounceV = 1.0 / static_cast<double>(a.firstBounceV);
       a.samples = ctx->samples.ptr;
+      a.mtHistory = ctx->mtHistory.ptr;
+      a.mtHistoryThreads = mtThreads;
+      a.mtStoreLimit = mtLimit;
       a.ticket = ctx->counters.ptr;
       a.castCounter = ctx->counters.ptr + 1;
       PT_CUDA(launchRenderKeyed(a, ctx->numSms, keyedConfig, ctx->stream));

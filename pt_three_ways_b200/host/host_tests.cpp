@@ -417,6 +417,8 @@ static void recipeTests(const std::string &scenesDir, const std::string &fixture
 // std::mt19937: first generation from the two running seed words, the prefetch hand-over of
 // the camera draws, and the in-place later generations.
 static void laneMt19937Tests() {
+  const uint32_t noLimit = mtStoreLimit(100000);
+  CHECK(noLimit == 0xffffffffu);
   for (uint32_t seed : {0u, 1u, 5489u, 0xffffffffu, 123456789u, 640u * 480u * 7u + 17u}) {
     for (uint32_t cameraWords : {4u, 8u}) {
       std::mt19937 reference(seed);
@@ -427,12 +429,31 @@ static void laneMt19937Tests() {
       rng.seed(seed);
       int bad = 0;
       for (uint32_t i = 0; i < cameraWords; ++i)
-        bad += rng.word<true>(history) != reference();
+        bad += rng.word<true>(history, noLimit) != reference();
       for (uint32_t i = 0; i < kMtPrefetchWords; ++i) // what the megakernel does when the sample starts
         history[i] = history[kMtWords + i];
       for (int i = 0; i < 3000; ++i)
-        bad += rng.word<false>(history) != reference();
+        bad += rng.word<false>(history, noLimit) != reference();
       CHECK(bad == 0);
+    }
+    // A sample that draws at most maxWords <= 624 words skips the stores nobody reads back.
+    for (uint32_t maxWords : {9u, 100u, 227u, 228u, 235u, 488u, 623u, 624u}) {
+      std::mt19937 reference(seed);
+      LaneMt19937 rng;
+      uint32_t history[kMtHistoryWords];
+      for (uint32_t &word : history)
+        word = 0xdeadbeefu;
+      rng.seed(seed);
+      const uint32_t limit = mtStoreLimit(maxWords);
+      int bad = 0;
+      for (uint32_t i = 0; i < 8; ++i)
+        bad += rng.word<true>(history, limit) != reference();
+      for (uint32_t i = 0; i < kMtPrefetchWords; ++i)
+        history[i] = history[kMtWords + i];
+      for (uint32_t i = 8; i < maxWords; ++i)
+        bad += rng.word<false>(history, limit) != reference();
+      CHECK(bad == 0);
+      CHECK(limit >= 624 || history[limit] == 0xdeadbeefu); // really skipped
     }
   }
   std::mt19937 defaultSeeded; // the standard's own known answer: 10000th output = 4123659995
@@ -441,7 +462,7 @@ static void laneMt19937Tests() {
   rng.seed(5489u);
   uint32_t last = 0;
   for (int i = 0; i < 10000; ++i)
-    last = rng.word<false>(history);
+    last = rng.word<false>(history, 0xffffffffu);
   CHECK(last == 4123659995u);
 }
 
