@@ -183,11 +183,6 @@ __device__ __forceinline__ uint32_t fpEngineSeed(uint32_t width, uint32_t height
   return height * width * static_cast<uint32_t>(passSeed) + static_cast<uint32_t>(px) * width +
          static_cast<uint32_t>(py);
 }
-__device__ __forceinline__ double fpCanonical(LaneMt19937 &rng, uint32_t *history, uint32_t storeLimit) {
-  const uint32_t lo = rng.word<false>(history, storeLimit);
-  const uint32_t hi = rng.word<false>(history, storeLimit);
-  return canonicalFromWords(lo, hi);
-}
 // Seeds the engine of a prefetched sample and draws its camera ray (Camera::randomRay draws two
 // doubles, rayFromUnit two more only when the aperture is open, Camera.h:30-33,56-58).  Always
 // executed by a batch of lanes together (see the megakernel), so out of line.
@@ -261,8 +256,8 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   bool stackSpecular[kMaxDepth];
   // fp way: this lane's engine, and the words it has generated (its slice of the scratch buffer).
   LaneMt19937 rng{0u, 0u, 0u};
-  uint32_t *const history =
-      kFp ? args.mtHistory + (static_cast<size_t>(blockIdx.x) * kBlock + threadIdx.x) * kMtHistoryStride : nullptr;
+  // (32-bit offset: the compiler re-derives this address at every use rather than hold it)
+  uint32_t *const history = kFp ? args.mtHistory + (blockIdx.x * kBlock + threadIdx.x) * kMtHistoryStride : nullptr;
   const uint32_t cameraWords = args.camera.apertureRadius == 0 ? 4u : 8u;
   const uint32_t storeLimit = args.mtStoreLimit;
 
@@ -374,6 +369,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     bool bounce = false;         // launch a bounce from `surface` (or from `primary` at depth 0)
     bool terminalPrimary = false;
     bool needSurface = false;
+    bool skippedTriple = false;
     V3 incoming = mk(0, 0, 0);
     HitInfo hit{};
     if (tracing) {
@@ -391,11 +387,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
           incoming = shadeTerm(materialOf(scene, hit.material), true, mk(0, 0, 0));
           ended = true;
           terminalPrimary = depth == 0;
-          if (kFp && depth > 0) { // ... and its (u, v, p) draws still advance the sample's engine
-#pragma unroll 1
-            for (int i = 0; i < 6; ++i)
-              rng.word<false>(history, storeLimit);
-          }
+          // fp way: ... and its (u, v, p) draws still advance the sample's engine.  They are
+          // taken at the bounce site below, right before the next stratum's own draws, where the
+          // lanes of the warp are together (this branch runs at ~5 of 32 lanes).
+          skippedTriple = kFp && depth > 0;
         } else {
           needSurface = true;
         }
@@ -485,14 +480,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       }
       double ru, rv, rp;
       if (kFp) { // toUVSample draws u then v, then p (src/fp/Render.cpp:97-102,116)
-        ru = rv = rp = 0;
+        uint32_t words[6] = {0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll 1
-        for (int i = 0; i < 3; ++i) { // one copy of the generator code: shift the draws through
-          const double drawn = fpCanonical(rng, history, storeLimit);
-          ru = rv;
-          rv = rp;
-          rp = drawn;
-        }
+        for (int triple = skippedTriple ? 0 : 1; triple < 2; ++triple) // one copy of the generator code
+          rng.six(history, storeLimit, words);
+        ru = canonicalFromWords(words[0], words[1]);
+        rv = canonicalFromWords(words[2], words[3]);
+        rp = canonicalFromWords(words[4], words[5]);
       } else {
         KeyedDraws{key0}.bounce(pixel, static_cast<uint32_t>(subPath), static_cast<uint32_t>(depth), ru, rv, rp);
       }
@@ -1080,7 +1074,8 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
   unsigned long long grid = static_cast<unsigned long long>(numSms) * perSm;
   if (wanted < grid)
     grid = wanted ? wanted : 1;
-  if (kWay == 1 && (args.mtHistory == nullptr || grid * kBlock > args.mtHistoryThreads))
+  if (kWay == 1 && (args.mtHistory == nullptr || grid * kBlock > args.mtHistoryThreads ||
+                    args.mtHistoryThreads * kMtHistoryStride > 0xffffffffull))
     return cudaErrorInvalidValue; // scratch for the per-lane engines: see mtHistoryThreadsFor()
   kernel<<<static_cast<unsigned>(grid), kBlock, smemBytes, stream>>>(args);
   return cudaGetLastError();

@@ -107,6 +107,41 @@ struct LaneMt19937 {
     ++k;
     return temper(w);
   }
+
+  // The next six outputs (three doubles: one (u, v, p) triple).  Straight-line and free of
+  // divergence while the six words lie inside the first generation (k + 6 <= 623, every group
+  // of the default configuration): lanes before and after word 227 differ by a predicated load.
+  PT_HD void six(uint32_t *history, uint32_t storeLimit, uint32_t (&out)[6]) {
+    if (k + 6 <= kMtWords - 1) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+      for (int i = 0; i < 6; ++i) {
+        const uint32_t next = lcg(a, k + 1);
+        const uint32_t source = k < kMtWords - kMtShift ? b : history[k - (kMtWords - kMtShift)];
+        b = lcg(b, k + kMtShift + 1); // unused once k >= 227
+        const uint32_t w = source ^ twist(a, next);
+        if (k < storeLimit)
+          history[k] = w;
+        a = next;
+        ++k;
+        out[i] = temper(w);
+      }
+    } else {
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+      for (int i = 0; i < 6; ++i) { // shift the outputs through: no dynamic register indexing
+        const uint32_t drawn = word<false>(history, storeLimit);
+        out[0] = out[1];
+        out[1] = out[2];
+        out[2] = out[3];
+        out[3] = out[4];
+        out[4] = out[5];
+        out[5] = drawn;
+      }
+    }
+  }
 };
 
 } // namespace ptb200

@@ -456,6 +456,33 @@ static void laneMt19937Tests() {
       CHECK(limit >= 624 || history[limit] == 0xdeadbeefu); // really skipped
     }
   }
+  // Groups of six (one (u, v, p) triple) through every regime: before/after word 227, across the
+  // end of the first generation and into the in-place generations, with and without skipped stores.
+  for (uint32_t seed : {7u, 0x9e3779b9u}) {
+    for (uint32_t cameraWords : {4u, 8u}) {
+      for (uint32_t groups : {80u, 103u, 400u}) {
+        std::mt19937 reference(seed);
+        LaneMt19937 rng;
+        uint32_t history[kMtHistoryWords];
+        for (uint32_t &word : history)
+          word = 0xdeadbeefu;
+        rng.seed(seed);
+        const uint32_t limit = mtStoreLimit(cameraWords + 6ull * groups);
+        int bad = 0;
+        for (uint32_t i = 0; i < cameraWords; ++i)
+          bad += rng.word<true>(history, 0u) != reference();
+        for (uint32_t i = 0; i < kMtPrefetchWords; ++i)
+          history[i] = history[kMtWords + i];
+        for (uint32_t g = 0; g < groups; ++g) {
+          uint32_t out[6] = {0, 0, 0, 0, 0, 0};
+          rng.six(history, limit, out);
+          for (uint32_t value : out)
+            bad += value != reference();
+        }
+        CHECK(bad == 0);
+      }
+    }
+  }
   std::mt19937 defaultSeeded; // the standard's own known answer: 10000th output = 4123659995
   LaneMt19937 rng;
   uint32_t history[kMtHistoryWords];

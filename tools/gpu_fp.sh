@@ -5,16 +5,19 @@ TAG=${1:-fp}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader | head -1
 timeout 900 python -m pytest tests/test_gpu_fp_way.py -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_tests.log
-timeout 300 python - <<'PY' 2>&1 | tee gpurun_out/${TAG}_rates.jsonl
-import json, sys
+cat > /tmp/fp_rates.py <<'PY'
+import json, os, sys
 sys.path.insert(0, ".")
 from pt_three_ways_b200 import capi, scenefile
-for name, w, h, spp in (("cornell", 640, 480, 64), ("cornell", 640, 480, 256), ("suzanne", 640, 480, 32), ("ce", 320, 180, 8)):
+cases = (("cornell", 640, 480, 64), ("cornell", 640, 480, 256), ("suzanne", 640, 480, 32), ("ce", 320, 180, 8))
+if os.environ.get("PTB200_KEYED_CONFIG"):
+    cases = cases[1:2]
+for name, w, h, spp in cases:
     scene = scenefile.load(f"tests/golden/scenes/{name}.ptscene")
     ctx = capi.Context(0)
     ctx.upload_scene(scene)
     cam = scene.camera(w, h)
-    row = {"scene": name, "w": w, "h": h, "spp": spp}
+    row = {"scene": name, "w": w, "h": h, "spp": spp, "config": os.environ.get("PTB200_KEYED_CONFIG", "auto")}
     for label, mode in (("keyed", capi.RNG_KEYED_PHILOX), ("fp", capi.RNG_MT19937_PER_PIXEL)):
         best = 0.0
         for _ in range(3):
@@ -25,6 +28,7 @@ for name, w, h, spp in (("cornell", 640, 480, 64), ("cornell", 640, 480, 256), (
     print(json.dumps(row), flush=True)
     ctx.close()
 PY
+(timeout 300 python /tmp/fp_rates.py; PTB200_KEYED_CONFIG=4 timeout 120 python /tmp/fp_rates.py) 2>&1 | tee gpurun_out/${TAG}_rates.jsonl
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python - <<'PY' 2>&1 | tail -6 | tee gpurun_out/${TAG}_memcheck.log
 import sys
 sys.path.insert(0, ".")
