@@ -99,6 +99,13 @@ typedef struct PtRenderParams {
                                             per pixel, strata are walked v-major and the emission is
                                             added after the average.  Exact AND parallel over pixels;
                                             the image is fp::render's with --max-cpus 1 */
+#define PTB200_RNG_MT19937_SEQUENTIAL_OO 3 /* the reference's `oo` way (`--way oo`, src/oo/Renderer.cpp:
+                                            60-107): the sequential stream and u-major strata of mode 1
+                                            with the estimator of mode 2 (sub-samples contribute
+                                            radiance(child) or diffuse*radiance(child); the emission is
+                                            added after the average; t == Epsilon is a hit,
+                                            src/oo/Triangle.cpp:31).  Parallel over passes only, like
+                                            mode 1; the image is oo::Renderer::render's with --max-cpus 1 */
 
 /* What a backend-specific caller may set beyond RenderParams.  Zero-initialise for defaults. */
 typedef struct PtRenderOptions {

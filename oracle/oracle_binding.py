@@ -18,6 +18,7 @@ REF_TOOL = os.path.join(HERE, "_ref", "ref_tool")
 RNG_KEYED_PHILOX = 0
 RNG_MT19937_SEQUENTIAL = 1
 RNG_FP_PER_PIXEL = 2  # the reference's `fp` way: mt19937 per (pass, pixel), src/fp/Render.cpp
+RNG_OO_SEQUENTIAL = 3  # the reference's `oo` way: dod's stream, fp's estimator, src/oo/Renderer.cpp
 
 _lib = None
 
@@ -144,6 +145,20 @@ def ref_fp_pass(scene, width, height, seed, tmpdir, first_u=4, first_v=4, max_de
     out = os.path.join(tmpdir, f"ref_fp_pass_{width}x{height}_{seed}.f64")
     ref_tool("fp-pass", scene, width, height, seed, first_u, first_v, max_depth, preview, out)
     return np.fromfile(out, dtype=np.float64).reshape(height, width, 3)
+
+
+def ref_oo_pass(scene, width, height, seed, pass_index, tmpdir, first_u=4, first_v=4, max_depth=5,
+                preview=0) -> np.ndarray:
+    """One pass image (H,W,3) from the reference's own oo::Renderer::radiance()/randomRay()."""
+    out = os.path.join(tmpdir, f"ref_oo_pass_{width}x{height}_{seed}_{pass_index}.f64")
+    ref_tool("oo-pass", scene, width, height, seed, pass_index, first_u, first_v, max_depth, preview, out)
+    return np.fromfile(out, dtype=np.float64).reshape(height, width, 3)
+
+
+def ref_oo_render(scene, width, height, spp, max_cpus, seed, out="-", first_u=4, first_v=4, max_depth=5) -> dict:
+    """Runs the unmodified oo::Renderer::render; returns its JSON line (seconds, total_samples)."""
+    return json.loads(ref_tool("oo-render", scene, width, height, spp, max_cpus, seed, first_u,
+                               first_v, max_depth, out))
 
 
 def ref_fp_render(scene, width, height, spp, max_cpus, seed, out="-", first_u=4, first_v=4, max_depth=5) -> dict:

@@ -39,13 +39,18 @@
 // because pixel values are sums of products of material constants selected by the discrete
 // hit sequence; see tests/test_oracle_golden.py).
 //
-// Two random-number policies:
+// Random-number / estimator policies:
 //   RNG_MT19937_SEQUENTIAL (1): one std::mt19937(seed+s) per pass consumed pixel after pixel
 //       in row-major order, exactly the reference stream (Scene.cpp:211-216).
 //   RNG_KEYED_PHILOX (0): Philox4x32-10 keyed by (seed+s) with counter
 //       (pixel, subPath, depth+1 | 0 for the camera, call); the same two-words-to-double rule.
 //       This is the throughput policy of the CUDA product; it is NOT the reference's stream
 //       (SURVEY.md section 0 item 3 explains why a per-pixel generator cannot be).
+//   RNG_MT19937_PER_PIXEL (2): the reference's `fp` way, one std::mt19937 per (pass, pixel)
+//       (src/fp/Render.cpp:76-135) -> radianceFp(uMajor = false).
+//   RNG_MT19937_SEQUENTIAL_OO (3): the reference's `oo` way (src/oo/Renderer.cpp:60-106):
+//       dod's per-pass sequential stream and u-major strata with the fp way's estimator
+//       (emission added after the average, t == Epsilon accepted) -> radianceFp(uMajor = true).
 // ============================================================================================
 #include <atomic>
 #include <cmath>
@@ -390,7 +395,8 @@ constexpr uint32_t PhiloxKeyHigh = 0xB200D0D0u;
 // One generator object per pass; a "site" (pixel, subPath, depth) is announced before each
 // group of draws.  The sequential policy ignores sites.
 struct Rng {
-  int mode; // 0 keyed Philox, 1 mt19937 sequential (one per pass), 2 mt19937 per sample (fp way)
+  int mode; // 0 keyed Philox, 1 mt19937 sequential (one per pass), 2 mt19937 per sample (fp way),
+            // 3 mt19937 sequential with the oo way's estimator
   Mt19937 mt;
   uint32_t key0;
   uint32_t pixel{0}, subPath{0}, level{0}, call{0};
@@ -570,8 +576,17 @@ V3 radiance(const Scene &scene, Rng &rng, uint32_t pixel, uint32_t subPath, V3 o
 //     emission (:66-73); the emission is added once, after the average:
 //     emission + sum / (numU*numV)  (:118);
 //   * hits come from fp::intersect (see intersect() above).
+//
+// uMajor = true is oo::Renderer::radiance (src/oo/Renderer.cpp:60-91) instead: the same
+// post-average emission (Material::totalEmission(result / (numU*numV)), :90 with
+// src/oo/Material.cpp:19-22; the sub-sample terms are MatteMaterial/ShinyMaterial::sample,
+// Material.cpp:28-67, i.e. radiance(child) or diffuse * radiance(child)) and the same
+// t == Epsilon acceptance (src/oo/Triangle.cpp:31), but with the strata walked u-major
+// (:79-80) like Scene.cpp:155-156.  The virtual calls (Material::sample, totalEmission) keep
+// GCC from contracting across them: diffuse * child, result += term, result * (1/n) and
+// emission + inbound are each rounded on their own.
 V3 radianceFp(const Scene &scene, Rng &rng, V3 origin, V3 direction, int depth, const Params &params,
-              Counters &counters) {
+              Counters &counters, bool uMajor = false) {
   const int numUSamples = depth == 0 ? params.firstBounceUSamples : 1;
   const int numVSamples = depth == 0 ? params.firstBounceVSamples : 1;
   if (depth >= params.maxDepth)
@@ -588,8 +603,11 @@ V3 radianceFp(const Scene &scene, Rng &rng, V3 origin, V3 direction, int depth, 
   const double reflectivity =
       mat.reflectivity < 0 ? reflectance(hit.normal, direction, iorFrom, iorTo) : mat.reflectivity;
   V3 incomingLight{0, 0, 0}; // accumulate(..., Vec3()): init = init + element, in order
-  for (int vSample = 0; vSample < numVSamples; ++vSample) {
-    for (int uSample = 0; uSample < numUSamples; ++uSample) {
+  const int numStrata = numUSamples * numVSamples;
+  for (int stratum = 0; stratum < numStrata; ++stratum) {
+    {
+      const int uSample = uMajor ? stratum / numVSamples : stratum % numUSamples;
+      const int vSample = uMajor ? stratum % numVSamples : stratum / numUSamples;
       const double u = (static_cast<double>(uSample) + rng.uniform(0, 1.0)) /
                        static_cast<double>(numUSamples);
       const double v = (static_cast<double>(vSample) + rng.uniform(0, 1.0)) /
@@ -599,16 +617,20 @@ V3 radianceFp(const Scene &scene, Rng &rng, V3 origin, V3 direction, int depth, 
         const V3 newDir =
             coneSample(reflect(hit.normal, direction), mat.reflectionConeAngleRadians, u, v);
         incomingLight = add(incomingLight, radianceFp(scene, rng, hit.position, newDir, depth + 1,
-                                                      params, counters));
+                                                      params, counters, uMajor));
       } else {
         const V3 newDir = hemisphereSample(basis, u, v);
-        const V3 child = radianceFp(scene, rng, hit.position, newDir, depth + 1, params, counters);
+        const V3 child = radianceFp(scene, rng, hit.position, newDir, depth + 1, params, counters, uMajor);
         incomingLight = add(incomingLight, V3{mat.diffuse.x * child.x, mat.diffuse.y * child.y,
                                               mat.diffuse.z * child.z});
       }
     }
   }
   const double reciprocal = 1.0 / static_cast<double>(numUSamples * numVSamples); // Vec3.h:51-54
+  if (uMajor) { // oo: Vec3::operator/ in radiance(), operator+ inside the virtual totalEmission()
+    const V3 average = scale(incomingLight, reciprocal);
+    return add(mat.emission, average);
+  }
   return {std::fma(incomingLight.x, reciprocal, mat.emission.x),
           std::fma(incomingLight.y, reciprocal, mat.emission.y),
           std::fma(incomingLight.z, reciprocal, mat.emission.z)};
@@ -631,7 +653,7 @@ void renderPass(const Scene &scene, const Camera &cam, const Params &params, int
   Rng rng(rngMode, static_cast<uint32_t>(params.seed + pass), &counters);
   for (int y = 0; y < params.height; ++y) {
     const bool selected = y >= rowBegin && (y - rowBegin) % rowStep == 0;
-    if (!selected && rngMode != 1)
+    if (!selected && rngMode != 1 && rngMode != 3)
       continue;
     for (int x = 0; x < params.width; ++x) {
       const uint32_t pixel = static_cast<uint32_t>(x + y * params.width);
@@ -640,8 +662,8 @@ void renderPass(const Scene &scene, const Camera &cam, const Params &params, int
         rng.reseed(fpPixelSeed(params, params.seed + pass, x, y));
       V3 origin, direction;
       cameraRandomRay(cam, x, y, rng, origin, direction);
-      const V3 colour = rngMode == 2
-                            ? radianceFp(scene, rng, origin, direction, 0, params, counters)
+      const V3 colour = rngMode == 2 || rngMode == 3
+                            ? radianceFp(scene, rng, origin, direction, 0, params, counters, rngMode == 3)
                             : radiance(scene, rng, pixel, 0, origin, direction, 0, params, counters);
       if (selected) {
         colours[3 * pixel + 0] = colour.x;

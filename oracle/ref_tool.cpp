@@ -17,6 +17,8 @@
 #include "fp/Render.h"
 #include "fp/SceneBuilder.h"
 #include "math/Camera.h"
+#include "oo/Renderer.h"
+#include "oo/SceneBuilder.h"
 #include "math/Vec3.h"
 #include "util/ArrayOutput.h"
 #include "util/MaterialSpec.h"
@@ -201,7 +203,9 @@ int usage() {
                "ref_tool render NAME W H SPP MAXCPUS SEED NU NV MAXDEPTH OUT.raw|-\n"
                "ref_tool intersect NAME|FILE.ptscene WHICH NEARER RAYS.f64 OUT.f64\n"
                "ref_tool fp-pass NAME W H SEED NU NV MAXDEPTH PREVIEW OUT.f64   (fp::render, one pass)\n"
-               "ref_tool fp-render NAME W H SPP MAXCPUS SEED NU NV MAXDEPTH OUT.raw|-\n";
+               "ref_tool fp-render NAME W H SPP MAXCPUS SEED NU NV MAXDEPTH OUT.raw|-\n"
+               "ref_tool oo-pass NAME W H SEED PASS NU NV MAXDEPTH PREVIEW OUT.f64   (oo::Renderer, one pass)\n"
+               "ref_tool oo-render NAME W H SPP MAXCPUS SEED NU NV MAXDEPTH OUT.raw|-\n";
   return 2;
 }
 
@@ -374,6 +378,60 @@ int main(int argc, char **argv) {
       std::streambuf *saved = std::cout.rdbuf(std::cerr.rdbuf());
       const auto t0 = std::chrono::steady_clock::now();
       ArrayOutput output = fp::render(cam, builder.scene(), p, [](const ArrayOutput &) {});
+      const auto t1 = std::chrono::steady_clock::now();
+      std::cout.rdbuf(saved);
+      const std::string outPath = argv[11];
+      if (outPath != "-")
+        output.save(absolutePath(outPath));
+      std::printf("{\"seconds\": %.6f, \"total_samples\": %zu, \"pixels\": %d}\n",
+                  std::chrono::duration<double>(t1 - t0).count(), output.totalSamples(),
+                  p.width * p.height);
+      return 0;
+    }
+    if (cmd == "oo-pass" && argc == 12) {
+      // The body of the per-pass lambda of oo::Renderer::render (src/oo/Renderer.cpp:97-107),
+      // driving the reference's own oo::Renderer::radiance() ("visible for testing",
+      // src/oo/Renderer.h:43) and Camera::randomRay().
+      RenderParams p = sized(std::atoi(argv[3]), std::atoi(argv[4]));
+      p.seed = std::atoi(argv[5]);
+      const int pass = std::atoi(argv[6]);
+      p.firstBounceUSamples = std::atoi(argv[7]);
+      p.firstBounceVSamples = std::atoi(argv[8]);
+      p.maxDepth = std::atoi(argv[9]);
+      p.preview = std::atoi(argv[10]) != 0;
+      oo::SceneBuilder builder;
+      Camera cam = makeScene(argv[2], builder, p.width, p.height);
+      oo::Renderer renderer(builder.scene(), cam, p);
+      std::vector<double> colours(static_cast<size_t>(p.width) * p.height * 3);
+      std::mt19937 rng(p.seed + pass);
+      for (int y = 0; y < p.height; ++y) {
+        for (int x = 0; x < p.width; ++x) {
+          auto ray = cam.randomRay(x, y, rng);
+          const Vec3 c = renderer.radiance(rng, ray, 0);
+          double *dst = &colours[3 * (static_cast<size_t>(x) + static_cast<size_t>(y) * p.width)];
+          dst[0] = c.x();
+          dst[1] = c.y();
+          dst[2] = c.z();
+        }
+      }
+      std::ofstream out(absolutePath(argv[11]), std::ios::binary);
+      out.write(reinterpret_cast<const char *>(colours.data()), colours.size() * 8);
+      return 0;
+    }
+    if (cmd == "oo-render" && argc == 12) {
+      RenderParams p = sized(std::atoi(argv[3]), std::atoi(argv[4]));
+      p.samplesPerPixel = std::atoi(argv[5]);
+      p.maxCpus = std::atoi(argv[6]);
+      p.seed = std::atoi(argv[7]);
+      p.firstBounceUSamples = std::atoi(argv[8]);
+      p.firstBounceVSamples = std::atoi(argv[9]);
+      p.maxDepth = std::atoi(argv[10]);
+      oo::SceneBuilder builder;
+      Camera cam = makeScene(argv[2], builder, p.width, p.height);
+      oo::Renderer renderer(builder.scene(), cam, p);
+      std::streambuf *saved = std::cout.rdbuf(std::cerr.rdbuf());
+      const auto t0 = std::chrono::steady_clock::now();
+      ArrayOutput output = renderer.render([](const ArrayOutput &) {}); // the unmodified entry point
       const auto t1 = std::chrono::steady_clock::now();
       std::cout.rdbuf(saved);
       const std::string outPath = argv[11];

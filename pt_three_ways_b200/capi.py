@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(PACKAGE_DIR, "libptb200.so")
 RNG_KEYED_PHILOX = 0
 RNG_MT19937_SEQUENTIAL = 1
 RNG_MT19937_PER_PIXEL = 2  # the reference's `fp` way
+RNG_MT19937_SEQUENTIAL_OO = 3  # the reference's `oo` way
 
 EXPORTS = [
     "ptb200_last_error", "ptb200_device_count", "ptb200_render", "ptb200_render_multi",

@@ -475,6 +475,14 @@ __device__ __forceinline__ V3 fpLevelRadiance(const MaterialView &mat, V3 incomi
             fma(incomingLight.z, reciprocal, e.z));
 }
 
+// The `oo` way's level value (src/oo/Renderer.cpp:90): Material::totalEmission(result / n) is
+// Vec3::operator/ (a multiply by the reciprocal, Vec3.h:51-54) in the caller and
+// emission + inbound inside a virtual function (src/oo/Material.cpp:19-22): rounded separately,
+// unlike fpLevelRadiance()'s fused form.
+__device__ __forceinline__ V3 ooLevelRadiance(const MaterialView &mat, V3 incomingLight, double reciprocal) {
+  return add(mat.emission(), scale(incomingLight, reciprocal));
+}
+
 // ---- TMA / mbarrier primitives (sm_90+ PTX; SASS: UBLKCP, SYNCS) ----------------------------
 __device__ __forceinline__ uint32_t smemAddress(const void *p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -632,6 +632,9 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
 };
 
 // Whole-warp Scene::intersect: lanes stride the primitive lists, then an argmin.
+// kAcceptEpsilon: oo::Triangle::intersect (src/oo/Triangle.cpp:31) rejects `t < Epsilon` where
+// Scene.cpp:94 accepts `t > Epsilon`.
+template <bool kAcceptEpsilon = false>
 __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o, V3 d, unsigned lane,
                                                  bool useSpheres, bool useTriangles,
                                                  double nearerThanLimit) {
@@ -667,8 +670,8 @@ __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o,
       const double2 *record = reinterpret_cast<const double2 *>(scene.triExact + 10 * static_cast<size_t>(index));
       const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
                     a4 = __ldg(record + 4);
-      testTriangle(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d,
-                   static_cast<int>(index), best);
+      testTriangle<kAcceptEpsilon>(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d,
+                                   static_cast<int>(index), best);
     }
   }
   // Warp argmin in the serial scans' order (t, sphere-before-triangle, index) with three
@@ -690,7 +693,10 @@ __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o,
   return best;
 }
 
-template <int kWarps>
+// kOo: the reference's `oo` way (src/oo/Renderer.cpp:60-107) walks the same stream in the same
+// order; its estimator differs from Scene::radiance in where the emission is added
+// (Material::totalEmission after the average, :90) and in accepting t == Epsilon.
+template <int kWarps, bool kOo>
 __global__ void __launch_bounds__(kWarps * 32)
     renderSequentialKernel(const __grid_constant__ SequentialArgs args) {
   __shared__ uint32_t mtState[kWarps][624];
@@ -738,7 +744,7 @@ __global__ void __launch_bounds__(kWarps * 32)
 
     while (!sampleDone) { // the keyed megakernel's state machine, one path at a time
       ++casts;
-      const Nearest best = warpIntersect(scene, origin, direction, lane, true, true, inf);
+      const Nearest best = warpIntersect<kOo>(scene, origin, direction, lane, true, true, inf);
       bool ended = false, bounce = false, terminalPrimary = false;
       V3 incoming = mk(0, 0, 0);
       Surface surface{};
@@ -755,7 +761,7 @@ __global__ void __launch_bounds__(kWarps * 32)
           // The deepest level draws its (u, v, p) triples and builds rays whose radiance is
           // Vec3() (Scene.cpp:128-129,157-175): consume the stream, contribute the emission.
           rng.skip(6u * static_cast<uint32_t>(depth == 0 ? numSub : 1), lane);
-          incoming = shadeTerm(mat, true, mk(0, 0, 0));
+          incoming = shadeTerm(mat, true, mk(0, 0, 0)); // oo: emission + (0 + .. + 0) * (1/n), the same value
           ended = true;
           terminalPrimary = depth == 0;
         } else {
@@ -776,7 +782,7 @@ __global__ void __launch_bounds__(kWarps * 32)
       if (ended) {
         colour = incoming;
         if (depth == 0) {
-          if (terminalPrimary) {
+          if (terminalPrimary && !kOo) {
             acc = mk(0, 0, 0);
             for (int k = 0; k < numSub; ++k)
               acc = add(acc, incoming);
@@ -784,12 +790,18 @@ __global__ void __launch_bounds__(kWarps * 32)
           }
           sampleDone = true;
         } else {
-          for (int level = depth - 1; level >= 1; --level)
-            incoming = shadeTerm(materialOf(scene, stackMaterial[level]), stackSpecular[level], incoming);
-          acc = add(acc, shadeTerm(materialOf(scene, primary.material), primarySpecular, incoming));
+          for (int level = depth - 1; level >= 1; --level) {
+            const MaterialView mat = materialOf(scene, stackMaterial[level]);
+            incoming = kOo ? ooLevelRadiance(mat, fpSubSampleTerm(mat, stackSpecular[level], incoming), 1.0)
+                           : shadeTerm(mat, stackSpecular[level], incoming);
+          }
+          const MaterialView primaryMat = materialOf(scene, primary.material);
+          acc = add(acc, kOo ? fpSubSampleTerm(primaryMat, primarySpecular, incoming)
+                             : shadeTerm(primaryMat, primarySpecular, incoming));
           ++subPath;
           if (subPath >= numSub) {
-            colour = scale(acc, invNumSub);
+            colour = kOo ? ooLevelRadiance(primaryMat, acc, invNumSub) // src/oo/Renderer.cpp:90
+                         : scale(acc, invNumSub);                      // Scene.cpp:178
             sampleDone = true;
           } else {
             depth = 0;
@@ -1138,7 +1150,12 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
 
 cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream) {
   const int blocks = (args.numPasses + kSequentialWarps - 1) / kSequentialWarps;
-  renderSequentialKernel<kSequentialWarps><<<blocks, kSequentialWarps * 32, 0, stream>>>(args);
+  if (args.way == 2)
+    renderSequentialKernel<kSequentialWarps, true><<<blocks, kSequentialWarps * 32, 0, stream>>>(args);
+  else if (args.way == 0)
+    renderSequentialKernel<kSequentialWarps, false><<<blocks, kSequentialWarps * 32, 0, stream>>>(args);
+  else
+    return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -47,6 +47,8 @@ struct SequentialArgs {
   int32_t width, height;
   int32_t seed, passBegin, numPasses;
   int32_t maxDepth, firstBounceU, firstBounceV, preview;
+  int32_t way;                     // 0: the dod estimator (Scene.cpp:124-179); 2: the `oo` way's
+                                   //    (src/oo/Renderer.cpp:60-91) on the same stream
   double *samples;                 // [passInBatch][height*width][3]
   unsigned long long *castCounter;
 };

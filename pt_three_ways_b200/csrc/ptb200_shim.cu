@@ -186,11 +186,12 @@ int validateParams(const PtRenderParams *p, const PtRenderOptions *o) {
     return fail(PTB200_EINVAL, "first-bounce sample counts must be positive");
   if (o) {
     if (o->rngMode != PTB200_RNG_KEYED_PHILOX && o->rngMode != PTB200_RNG_MT19937_SEQUENTIAL &&
-        o->rngMode != PTB200_RNG_MT19937_PER_PIXEL)
+        o->rngMode != PTB200_RNG_MT19937_PER_PIXEL && o->rngMode != PTB200_RNG_MT19937_SEQUENTIAL_OO)
       return fail(PTB200_EINVAL, "unknown rngMode %d", o->rngMode);
     if (o->rowStep < 0 || o->rowBegin < 0)
       return fail(PTB200_EINVAL, "negative row partition");
-    if (o->rngMode == PTB200_RNG_MT19937_SEQUENTIAL && (o->rowBegin != 0 || o->rowStep > 1))
+    if ((o->rngMode == PTB200_RNG_MT19937_SEQUENTIAL || o->rngMode == PTB200_RNG_MT19937_SEQUENTIAL_OO) &&
+        (o->rowBegin != 0 || o->rowStep > 1))
       return fail(PTB200_EINVAL,
                   "the sequential mt19937 stream cannot be partitioned by rows; partition passes");
   }
@@ -432,7 +433,8 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
   const uint32_t ownPixels = ownRows * static_cast<uint32_t>(params->width);
   if (ownPixels == 0 || numPasses == 0)
     return PTB200_OK;
-  const bool sequential = opt.rngMode == PTB200_RNG_MT19937_SEQUENTIAL;
+  const bool ooWay = opt.rngMode == PTB200_RNG_MT19937_SEQUENTIAL_OO;
+  const bool sequential = opt.rngMode == PTB200_RNG_MT19937_SEQUENTIAL || ooWay;
   const size_t pixelsPerPass = sequential ? static_cast<size_t>(params->width) * params->height : ownPixels;
   size_t passesPerBatch = std::max<size_t>(1, kSampleBufferBytes / (pixelsPerPass * 24));
   if (opt.passesPerBatch > 0)
@@ -488,6 +490,7 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.firstBounceU = params->firstBounceUSamples;
       a.firstBounceV = params->firstBounceVSamples;
       a.preview = params->preview;
+      a.way = ooWay ? 2 : 0;
       a.samples = ctx->samples.ptr;
       a.castCounter = ctx->counters.ptr + 1;
       PT_CUDA(launchRenderSequential(a, ctx->stream));
@@ -694,7 +697,8 @@ int ptb200_render_multi(const PtScene *scene, const PtCamera *camera, const PtRe
     return fail(PTB200_EINVAL, "render_multi partitions rows itself; leave rowBegin/rowStep zero");
   const int n = static_cast<int>(list.size());
   const size_t pixels = static_cast<size_t>(params->width) * params->height;
-  const bool sequential = base.rngMode == PTB200_RNG_MT19937_SEQUENTIAL;
+  const bool sequential = base.rngMode == PTB200_RNG_MT19937_SEQUENTIAL ||
+                          base.rngMode == PTB200_RNG_MT19937_SEQUENTIAL_OO;
 
   struct Part {
     std::vector<PtPixel> pixels;

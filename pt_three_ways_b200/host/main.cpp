@@ -1,7 +1,7 @@
 // pt_b200 — command-line driver with the reference CLI's flags (src/main/main.cpp:382-404):
 //   -w/--width -h/--height --max-cpus --spp --first-bounce-u --first-bounce-v --max-depth
 //   --seed --preview --save-every --way --scene --raw <output>
-// (--way dod|fp) plus backend flags:  --rng keyed|exact   --gpus N (0 = all)   --scenes DIR   --device K
+// (--way dod|fp|oo) plus backend flags:  --rng keyed|exact   --gpus N (0 = all)   --scenes DIR   --device K
 //   --ptscene FILE (a PTSCENE2 fixture instead of --scene: the reference loader's own output,
 //   usable where the OBJ files are not available).
 // Scene building, OBJ/MTL loading, the framebuffer and the PNG/raw writers are host C++ here
@@ -90,7 +90,7 @@ Camera loadPtScene(const std::string &path, Scene &scene, int width, int height)
 int usage(const char *argv0) {
   std::cerr << "usage: " << argv0
             << " [-w W] [-h H] [--spp N] [--max-cpus N] [--first-bounce-u N] [--first-bounce-v N]\n"
-               "       [--max-depth N] [--seed N] [--preview] [--save-every SECS] [--way dod|fp]\n"
+               "       [--max-depth N] [--seed N] [--preview] [--save-every SECS] [--way dod|fp|oo]\n"
                "       [--scene NAME] [--raw] [--rng keyed|exact] [--gpus N] [--device K]\n"
                "       [--scenes DIR] <output>\n";
   return 1;
@@ -149,9 +149,10 @@ int main(int argc, const char *argv[]) {
     return usage(argv[0]);
   }
   // --way dod (default): the dod estimator with --rng keyed|exact.  --way fp: the reference's
-  // fp way (src/fp/Render.cpp), one mt19937 per pass and pixel — exact and parallel.
-  if (way != "dod" && way != "b200" && way != "fp") {
-    std::cerr << "Unknown way " << way << " (this backend renders the dod and fp ways only)\n";
+  // fp way (src/fp/Render.cpp), one mt19937 per pass and pixel — exact and parallel.  --way oo:
+  // the reference's oo way (src/oo/Renderer.cpp), always its exact per-pass stream.
+  if (way != "dod" && way != "b200" && way != "fp" && way != "oo") {
+    std::cerr << "Unknown way " << way << "\n"; // main.cpp:365
     return 1;
   }
   if (renderParams.seed == 0) { // main.cpp:426-429
@@ -192,8 +193,9 @@ int main(int argc, const char *argv[]) {
                         : loadPtScene(ptsceneFile, scene, renderParams.width, renderParams.height);
     std::cout << "Scene contains " << scene.numTriangles() << " triangles and "
               << scene.numSpheres() << " spheres.\n"; // main.cpp:320-323
-    scene.setRngMode(way == "fp" ? PTB200_RNG_MT19937_PER_PIXEL
-                                 : rng == "exact" ? PTB200_RNG_MT19937_SEQUENTIAL : PTB200_RNG_KEYED_PHILOX);
+    scene.setRngMode(way == "fp"   ? PTB200_RNG_MT19937_PER_PIXEL
+                     : way == "oo" ? PTB200_RNG_MT19937_SEQUENTIAL_OO
+                     : rng == "exact" ? PTB200_RNG_MT19937_SEQUENTIAL : PTB200_RNG_KEYED_PHILOX);
     scene.setDevice(device);
     scene.setUseAllDevices(gpus != 1);
 

@@ -12,6 +12,8 @@ Outputs (all small, committed):
   render_asis_cornell.raw   what the unmodified dod::Scene::render returns (raw format)
   fp_pass_<case>.npy        one whole-screen pass of the reference's `fp` way (fp::render, spp 1)
   fp_render_cornell.raw     the unmodified fp::render, 16x16, 5 spp, --max-cpus 1, seed 3
+  oo_pass_<case>.npy        per-pass images from the reference's oo::Renderer::radiance()/randomRay()
+  oo_render_asis_cornell.raw  what the unmodified oo::Renderer::render returns (16x16, 6 spp asked)
 """
 import json
 import os
@@ -43,6 +45,8 @@ PASS_CASES = [
     ("example1_24x18_s6_p0", "example1", 24, 18, 6, 0, 4, 4, 5, 0),
     ("bbc-owl_24x18_s8_p0", "bbc-owl", 24, 18, 8, 0, 4, 4, 5, 0),
 ]
+# The `oo` way (src/oo/Renderer.cpp) walks the same stream as dod: the same cases.
+OO_PASS_CASES = PASS_CASES
 # (case name, scene, width, height, seed, firstU, firstV, maxDepth, preview): src/fp/Render.cpp
 FP_PASS_CASES = [
     ("cornell_32x24_s1", "cornell", 32, 24, 1, 4, 4, 5, 0),
@@ -118,6 +122,12 @@ def main():
             np.save(os.path.join(GOLDEN, f"fp_pass_{case}.npy"), img)
             print("fp", case, float(img.min()), float(img.max()))
         print(ob.ref_fp_render("cornell", 16, 16, 5, 1, 3, os.path.join(GOLDEN, "fp_render_cornell.raw")))
+        # The `oo` way: its own radiance() per pass, and its unmodified entry point.
+        for case, scene, w, h, seed, p, fu, fv, depth, preview in OO_PASS_CASES:
+            img = ob.ref_oo_pass(scene, w, h, seed, p, tmp, fu, fv, depth, preview)
+            np.save(os.path.join(GOLDEN, f"oo_pass_{case}.npy"), img)
+            print("oo", case, float(img.min()), float(img.max()))
+        print(ob.ref_oo_render("cornell", 16, 16, 6, 1, 2, os.path.join(GOLDEN, "oo_render_asis_cornell.raw")))
 
 
 if __name__ == "__main__":

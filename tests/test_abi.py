@@ -75,6 +75,13 @@ def test_argument_validation_precedes_device_use(capi, scenes):
         capi.render(scene, cam, capi.make_params(8, 6),
                     capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL, row_begin=1, row_step=2))
     assert err.value.code == 1 and "partition passes" in str(err.value)
+    with pytest.raises(capi.Ptb200Error) as err:
+        capi.render(scene, cam, capi.make_params(8, 6),
+                    capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL_OO, row_begin=1, row_step=2))
+    assert err.value.code == 1 and "partition passes" in str(err.value)
+    with pytest.raises(capi.Ptb200Error) as err:
+        capi.render(scene, cam, capi.make_params(8, 6), capi.make_options(rng_mode=4))
+    assert err.value.code == 1 and "unknown rngMode" in str(err.value)
 
 
 def test_product_does_not_touch_the_oracle():

@@ -27,7 +27,7 @@ def test_cli_rejects_bad_arguments():
         subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
     res = subprocess.run([exe], capture_output=True, text=True)
     assert res.returncode == 1 and "Missing output filename" in res.stderr
-    res = subprocess.run([exe, "--way", "oo", "out.png"], capture_output=True, text=True)
+    res = subprocess.run([exe, "--way", "smallpt", "out.png"], capture_output=True, text=True)
     assert res.returncode == 1 and "Unknown way" in res.stderr
     res = subprocess.run([exe, "--scene", "nonesuch", "--scenes", "/nonexistent", "out.png"],
                          capture_output=True, text=True)

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from tests.golden.make_golden import FP_PASS_CASES, PASS_CASES, SCENES
+from tests.golden.make_golden import FP_PASS_CASES, OO_PASS_CASES, PASS_CASES, SCENES
 
 
 def load_npy(golden_dir, name):
@@ -85,6 +85,48 @@ def test_fp_way_engine_seed_uses_the_reference_indexing(scenes, oracle):
     dod = osc.render(cam, oracle.params_array(w, h, spp=2, seed=1), oracle.RNG_MT19937_SEQUENTIAL, per_pass=True)
     assert not np.array_equal(fp["per_pass"][0], dod["per_pass"][0])
     assert fp["casts"] > 0 and abs(fp["casts"] / dod["casts"] - 1) < 0.2
+
+
+# ---- the reference's `oo` way (src/oo/Renderer.cpp): dod's stream, post-average emission -------
+@pytest.mark.parametrize("case", OO_PASS_CASES, ids=lambda c: c[0])
+def test_oo_way_pass_image_matches_reference(case, scenes, oracle, golden_dir):
+    """Golden: the per-pass lambda of oo::Renderer::render (Renderer.cpp:97-107) driving the
+    reference's own oo::Renderer::radiance(), built from src/oo/*.cpp."""
+    name, scene_name, w, h, seed, p, fu, fv, depth, preview = case
+    want = load_npy(golden_dir, f"oo_pass_{name}.npy")
+    scene = scenes[scene_name]
+    params = oracle.params_array(w, h, spp=1, seed=seed, max_depth=depth, first_u=fu, first_v=fv, preview=preview)
+    got = oracle.OracleScene(scene).render(scene.camera(w, h), params, oracle.RNG_OO_SEQUENTIAL, pass_begin=p,
+                                           num_passes=1, per_pass=True)["per_pass"][0]
+    assert np.abs(got - want).max() <= 1e-12  # measured: exactly 0
+
+
+def test_oo_way_unmodified_render_is_the_sum_of_the_passes_it_kept(scenes, oracle, golden_dir):
+    """oo::Renderer::render has dod's scheduler (Renderer.cpp:109-141): it leaves its loop once the
+    last pass has been LAUNCHED, so with --max-cpus 1 it returns passes 0..k-1 for some k <= spp."""
+    sums, counts = oracle.read_raw(os.path.join(golden_dir, "oo_render_asis_cornell.raw"))
+    kept = int(counts[0, 0])
+    assert (counts == kept).all() and 1 <= kept <= 6
+    scene = scenes["cornell"]
+    got = oracle.OracleScene(scene).render(scene.camera(16, 16), oracle.params_array(16, 16, spp=kept, seed=2),
+                                           oracle.RNG_OO_SEQUENTIAL)
+    assert np.array_equal(got["counts"], counts.astype(np.uint64))
+    assert np.abs(got["sums"] - sums).max() <= 1e-11
+
+
+def test_oo_way_differs_from_dod_only_in_rounding(scenes, oracle):
+    """Same stream, same strata order, same hits: the two estimators are algebraically equal
+    (emission + mean(terms) vs mean(emission + terms)), so the images agree to rounding but not
+    bit for bit — which is why `oo` is its own policy and not an alias of the sequential one."""
+    scene = scenes["cornell"]
+    w, h = 32, 24
+    cam = scene.camera(w, h)
+    osc = oracle.OracleScene(scene)
+    oo = osc.render(cam, oracle.params_array(w, h, spp=2, seed=1), oracle.RNG_OO_SEQUENTIAL)
+    dod = osc.render(cam, oracle.params_array(w, h, spp=2, seed=1), oracle.RNG_MT19937_SEQUENTIAL)
+    assert oo["casts"] == dod["casts"] and oo["rng_words"] == dod["rng_words"]
+    diff = np.abs(oo["sums"] - dod["sums"]).max()
+    assert 0 < diff <= 1e-12
 
 
 # ---- intersection records --------------------------------------------------------------------

@@ -98,3 +98,35 @@ def test_fp_way_unmodified_render_entry_point(ref, tmp_path):
     got = ref.OracleScene(scene).render(scene.camera(16, 16), ref.params_array(16, 16, spp=6, seed=3),
                                         ref.RNG_FP_PER_PIXEL)
     assert np.abs(got["sums"] - sums).max() <= 1e-10 * max(1.0, float(np.abs(sums).max()))
+
+
+@pytest.mark.parametrize("seed,kw", [(4, {}), (5, dict(first_u=3, first_v=2, max_depth=7)), (6, dict(max_depth=2)),
+                                     (8, dict(first_u=1, first_v=5, max_depth=9))])
+def test_oo_way_pass_images_match_the_reference_binary(seed, kw, ref, tmp_path):
+    """The reference's `oo` way (oo::Renderer::radiance built from src/oo/*.cpp) against the
+    oracle's RNG_OO_SEQUENTIAL policy, on random scenes."""
+    scene = random_scenes.random_scene(seed, num_triangles=20, num_spheres=3)
+    path = str(tmp_path / "scene.ptscene")
+    scenefile.save(scene, path)
+    w, h = 24, 18
+    for p in (0, 3):
+        want = ref.ref_oo_pass(path, w, h, 11, p, str(tmp_path), kw.get("first_u", 4), kw.get("first_v", 4),
+                               kw.get("max_depth", 5))
+        got = ref.OracleScene(scene).render(scene.camera(w, h), ref.params_array(w, h, spp=1, seed=11, **kw),
+                                            ref.RNG_OO_SEQUENTIAL, pass_begin=p, num_passes=1,
+                                            per_pass=True)["per_pass"][0]
+        assert np.abs(got - want).max() <= 1e-11 * max(1.0, float(np.abs(want).max()))
+
+
+def test_oo_way_unmodified_render_entry_point(ref, tmp_path):
+    scene = random_scenes.random_scene(7, num_triangles=12, num_spheres=2)
+    path = str(tmp_path / "scene.ptscene")
+    scenefile.save(scene, path)
+    out = str(tmp_path / "oo.raw")
+    ref.ref_oo_render(path, 16, 16, 6, 1, 3, out)
+    sums, counts = ref.read_raw(out)
+    kept = int(counts[0, 0])
+    assert (counts == kept).all() and 1 <= kept <= 6
+    got = ref.OracleScene(scene).render(scene.camera(16, 16), ref.params_array(16, 16, spp=kept, seed=3),
+                                        ref.RNG_OO_SEQUENTIAL)
+    assert np.abs(got["sums"] - sums).max() <= 1e-10 * max(1.0, float(np.abs(sums).max()))
