@@ -196,6 +196,7 @@ def render(scene, camera18, params: PtRenderParams, options: PtRenderOptions | N
 
 
 SWEEP_ONE_STAGE, SWEEP_TWO_STAGE_FP64, SWEEP_FP32_STAGE0, SWEEP_FP32X2_STAGE0, SWEEP_FP32X2_STAGE0_T = 0, 1, 2, 3, 4
+SWEEP_FP32X2_SIGNS_T, SWEEP_FP32X2_SIGNS = 5, 6  # 4 and 3 with the stage-0 decisions kept in sign bits
 
 
 def intersect(scene, rays, which=0, nearer_than=float("inf"), device=0, warp_cooperative=False,

@@ -255,6 +255,7 @@ __device__ __forceinline__ bool stage0Keep(float v0x, float v0y, float v0z, floa
 // new on sm_100): .x holds triangle i, .y triangle i+1.  Returns bit 0 / bit 1.
 struct Stage0Ray2 {
   float2 ox, oy, oz, dx, dy, dz; // each component duplicated into both halves
+  uint32_t one;                  // 0x3f800000 held in a register (stage0Reject2)
 };
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 template <bool kRejectNegativeT>
@@ -304,7 +305,7 @@ __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter
   const Stage0Ray r{static_cast<float>(o.x), static_cast<float>(o.y), static_cast<float>(o.z),
                     static_cast<float>(d.x), static_cast<float>(d.y), static_cast<float>(d.z)};
   const Stage0Ray2 r2{make_float2(r.ox, r.ox), make_float2(r.oy, r.oy), make_float2(r.oz, r.oz),
-                      make_float2(r.dx, r.dx), make_float2(r.dy, r.dy), make_float2(r.dz, r.dz)};
+                      make_float2(r.dx, r.dx), make_float2(r.dy, r.dy), make_float2(r.dz, r.dz), 0u};
 #pragma unroll 1
   for (int chunk = 0; chunk < count; chunk += 64) {
     const int chunkEnd = min(count, chunk + 64);
@@ -339,6 +340,119 @@ __device__ __forceinline__ void sweepTileStage0(const float *__restrict__ filter
     while (survivors) {
       const int i = chunk + __ffsll(static_cast<long long>(survivors)) - 1;
       survivors &= survivors - 1;
+      const double2 *record = reinterpret_cast<const double2 *>(exact + 10 * static_cast<size_t>(i));
+      const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
+                    a4 = __ldg(record + 4);
+      testTriangle<kFpWay>(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d, firstIndex + i, best);
+    }
+  }
+}
+
+// ---- the same stage 0 with its decision kept in SIGN BITS (sweep variants 5 and 6) -------------
+// stage0Keep2() spends as many instructions on its comparisons (FSETP/SEL/LOP3, one triangle at
+// a time) as on its arithmetic.  Every one of its tests is the sign of a difference, and an IEEE
+// subtraction never gets a sign wrong, so the tests are evaluated two triangles at a time in the
+// packed datapath and combined as integers:
+//   with s = copysign(1, det32) (s*x is exact):
+//     a = s*X32 + 2Ex  (< 0  <=>  s*X32 < -2Ex)        b = s*Y32 + 2Ey        c = s*T32 + 2Et
+//     e = K - s*(X32+Y32),  K = |det32|(1+2^-20) + K3   (< 0  <=>  s*(X32+Y32) > K)
+//     f = Ed - |det32|                                  (< 0  <=>  |det32| > Ed)
+//   certainly rejected  <=>  sign bit of  (a | b | c | e) & f.
+// These are the decisions of stage0Keep2<kRejectNegativeT>() bit for bit (none of the sums can be
+// -0: the bounds are >= +0 or, for padding triangles, -1 with det32 == 0), except that a NaN no
+// longer forces "keep": a NaN needs a non-finite ray or an FP32 overflow (excluded by the
+// coordinate range check at upload), and the exact test never accepts a triangle whose
+// arithmetic involves a NaN (Scene.cpp:89,94 compare false).
+template <bool kRejectNegativeT>
+__device__ __forceinline__ void stage0Reject2(float2 v0x, float2 v0y, float2 v0z, float2 e1x, float2 e1y,
+                                              float2 e1z, float2 e2x, float2 e2y, float2 e2z, float2 ed,
+                                              float2 kx, float2 ky, float2 k3, float2 kt,
+                                              const Stage0Ray2 &r, uint32_t &rejectA, uint32_t &rejectB) {
+  const float2 px = __ffma2_rn(r.dy, e2z, neg2(__fmul2_rn(r.dz, e2y)));
+  const float2 py = __ffma2_rn(r.dz, e2x, neg2(__fmul2_rn(r.dx, e2z)));
+  const float2 pz = __ffma2_rn(r.dx, e2y, neg2(__fmul2_rn(r.dy, e2x)));
+  const float2 det = __ffma2_rn(e1z, pz, __ffma2_rn(e1y, py, __fmul2_rn(e1x, px)));
+  const float2 tx = __fadd2_rn(r.ox, neg2(v0x)), ty = __fadd2_rn(r.oy, neg2(v0y)),
+               tz = __fadd2_rn(r.oz, neg2(v0z));
+  const float2 x = __ffma2_rn(tz, pz, __ffma2_rn(ty, py, __fmul2_rn(tx, px)));
+  const float2 qx = __ffma2_rn(ty, e1z, neg2(__fmul2_rn(tz, e1y)));
+  const float2 qy = __ffma2_rn(tz, e1x, neg2(__fmul2_rn(tx, e1z)));
+  const float2 qz = __ffma2_rn(tx, e1y, neg2(__fmul2_rn(ty, e1x)));
+  const float2 y = __ffma2_rn(r.dz, qz, __ffma2_rn(r.dy, qy, __fmul2_rn(r.dx, qx)));
+  // copysign(1, det): (det & 0x80000000) | 0x3f800000 as ONE three-input logic instruction; `one`
+  // arrives in a register (a LOP3 takes a single immediate).
+  uint32_t sA, sB;
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(sA) : "r"(__float_as_uint(det.x)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(sB) : "r"(__float_as_uint(det.y)), "r"(r.one));
+  const float2 s = make_float2(__uint_as_float(sA), __uint_as_float(sB));
+  const float2 adet = make_float2(fabsf(det.x), fabsf(det.y));
+  const float2 a = __ffma2_rn(x, s, kx);
+  const float2 b = __ffma2_rn(y, s, ky);
+  const float2 bound = __ffma2_rn(adet, make_float2(1.0f + 0x1p-20f, 1.0f + 0x1p-20f), k3);
+  const float2 e = __ffma2_rn(neg2(__fadd2_rn(x, y)), s, bound);
+  const float2 f = __fadd2_rn(ed, neg2(adet));
+  uint32_t anyA = __float_as_uint(a.x) | __float_as_uint(b.x) | __float_as_uint(e.x);
+  uint32_t anyB = __float_as_uint(a.y) | __float_as_uint(b.y) | __float_as_uint(e.y);
+  if (kRejectNegativeT) {
+    const float2 t = __ffma2_rn(e2z, qz, __ffma2_rn(e2y, qy, __fmul2_rn(e2x, qx)));
+    const float2 c = __ffma2_rn(t, s, kt);
+    anyA |= __float_as_uint(c.x);
+    anyB |= __float_as_uint(c.y);
+  }
+  rejectA = anyA & __float_as_uint(f.x);
+  rejectB = anyB & __float_as_uint(f.y);
+}
+
+// Sweeps a staged FP32 tile with stage0Reject2().  The decisions of a chunk of 64 triangles are
+// shifted into one 64-bit register, four at a time (first triangle ends up in the highest bit), so
+// a small scene still has ONE survivor loop per cast, which the lanes of a warp walk together.
+// Survivors are taken from the top bit down: ascending index, the serial loop's tie-break order.
+template <bool kRejectNegativeT, bool kFpWay = false>
+__device__ __forceinline__ void sweepTileStage0Signs(const float *__restrict__ filter,
+                                                     const double *__restrict__ exact, int count,
+                                                     int firstIndex, V3 o, V3 d, Nearest &best) {
+  const Stage0Ray r{static_cast<float>(o.x), static_cast<float>(o.y), static_cast<float>(o.z),
+                    static_cast<float>(d.x), static_cast<float>(d.y), static_cast<float>(d.z)};
+  uint32_t one;
+  asm("mov.u32 %0, 0x3f800000;" : "=r"(one)); // opaque to constant folding: see stage0Reject2
+  const Stage0Ray2 r2{make_float2(r.ox, r.ox), make_float2(r.oy, r.oy), make_float2(r.oz, r.oz),
+                      make_float2(r.dx, r.dx), make_float2(r.dy, r.dy), make_float2(r.dz, r.dz), one};
+#pragma unroll 1
+  for (int chunk = 0; chunk < count; chunk += 64) {
+    const int chunkEnd = min(count, chunk + 64);
+    uint32_t rejectedHi = 0xffffffffu, rejectedLo = 0xffffffffu;
+    const float4 *group = reinterpret_cast<const float4 *>(filter) + (chunk >> 2) * kFilterFloats;
+    const float4 *const groupEnd = reinterpret_cast<const float4 *>(filter) + (chunkEnd >> 2) * kFilterFloats;
+#pragma unroll 1
+    for (; group != groupEnd; group += kFilterFloats) {
+      float4 a[kFilterFloats];
+#pragma unroll
+      for (int k = 0; k < kFilterFloats; ++k)
+        a[k] = group[k];
+      uint32_t r0, r1, r2bits, r3;
+#define PT_LO(k) make_float2(a[k].x, a[k].y)
+#define PT_HI(k) make_float2(a[k].z, a[k].w)
+      stage0Reject2<kRejectNegativeT>(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6),
+                                      PT_LO(7), PT_LO(8), PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), PT_LO(13),
+                                      r2, r0, r1);
+      stage0Reject2<kRejectNegativeT>(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6),
+                                      PT_HI(7), PT_HI(8), PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), PT_HI(13),
+                                      r2, r2bits, r3);
+#undef PT_LO
+#undef PT_HI
+      rejectedHi = __funnelshift_l(rejectedLo, rejectedHi, 4);
+      rejectedLo = __funnelshift_l(r0, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r1, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r2bits, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r3, rejectedLo, 1);
+    }
+    // left-align: triangle chunk + k at bit 63 - k; the slots past chunkEnd read "rejected"
+    unsigned long long keep = ~((static_cast<unsigned long long>(rejectedHi) << 32) | rejectedLo)
+                              << (64 - (chunkEnd - chunk));
+    while (keep) {
+      const int k = __clzll(static_cast<long long>(keep));
+      keep &= ~(0x8000000000000000ull >> k);
+      const int i = chunk + k;
       const double2 *record = reinterpret_cast<const double2 *>(exact + 10 * static_cast<size_t>(i));
       const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
                     a4 = __ldg(record + 4);

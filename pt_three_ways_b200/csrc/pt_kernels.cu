@@ -131,7 +131,10 @@ __device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const 
                                                 uint32_t tileIndex, V3 o, V3 d, Nearest &best) {
   const int tileTris = static_cast<int>(scene.tileTris);
   const int first = static_cast<int>(tileIndex * scene.tileTris);
-  if (kSweep >= 2)
+  if (kSweep >= 5)
+    sweepTileStage0Signs<kSweep == 5, kFpWay>(reinterpret_cast<const float *>(tile),
+                    scene.triExact + static_cast<size_t>(first) * 10, tileTris, first, o, d, best);
+  else if (kSweep >= 2)
     sweepTileStage0<kSweep >= 3, kSweep == 4, kFpWay>(reinterpret_cast<const float *>(tile),
                     scene.triExact + static_cast<size_t>(first) * 10, tileTris, tileTris, first, o, d, best);
   else if (kSweep == 1)
@@ -919,7 +922,11 @@ __global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
     if (args.which != 1) {
       for (uint32_t j = 0; j < scene.numTiles; ++j) {
         const unsigned char *tile = stream.acquire();
-        if (args.sweep == 4)
+        if (args.sweep == 6)
+          sweepStagedTile<6>(scene, tile, j, o, d, best);
+        else if (args.sweep == 5)
+          sweepStagedTile<5>(scene, tile, j, o, d, best);
+        else if (args.sweep == 4)
           sweepStagedTile<4>(scene, tile, j, o, d, best);
         else if (args.sweep == 3)
           sweepStagedTile<3>(scene, tile, j, o, d, best);
@@ -1096,9 +1103,10 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
 // A megakernel configuration is 10 * launchShape + sweepVariant.
 //   sweep variants: 0 one-stage FP64; 1 two-stage FP64 (prefilter + exact); 2 FP32 stage 0 + exact;
 //                   3 the same with the packed FP32x2 datapath (FFMA2); 4 = 3 + stage 0 also
-//                   rejects triangles certainly behind the ray (pays off on small scenes)
+//                   rejects triangles certainly behind the ray (pays off on small scenes);
+//                   5 = 4 and 6 = 3 with the stage-0 decisions kept in sign bits (stage0Reject2)
 //   launch shapes:  0 = 256 threads x 2 CTAs/SM (128 registers); 1 = 384 x 1 (168 registers);
-//                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5; 5 = 192 x 3
+//                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5 (96 registers); 5 = 192 x 3
 // Default (measured on B200, profiles/): packed FP32 stage 0 everywhere it is usable; three CTAs
 // per SM for small scenes, where shading latency rather than the sweep limits the kernel.
 // PTB200_KEYED_CONFIG overrides it (tools/sweep_configs.py).
@@ -1119,12 +1127,15 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
 size_t mtHistoryThreadsFor(int numSms) { return static_cast<size_t>(numSms) * 768; }
 
 cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream) {
-  if (args.way == 1) { // the fp way: the default configurations and the unfiltered fallback only
+  if (args.way == 1) { // the fp way: the default configurations, the unfiltered fallback, sign-bit stage 0
     switch (config) {
     case 1: return launchKeyedConfig<256, 2, 1, 1>(args, numSms, stream);
     case 3: return launchKeyedConfig<256, 2, 3, 1>(args, numSms, stream);
     case 4: return launchKeyedConfig<256, 2, 4, 1>(args, numSms, stream);
     case 24: return launchKeyedConfig<256, 3, 4, 1>(args, numSms, stream);
+    case 5: return launchKeyedConfig<256, 2, 5, 1>(args, numSms, stream);
+    case 25: return launchKeyedConfig<256, 3, 5, 1>(args, numSms, stream);
+    case 45: return launchKeyedConfig<128, 5, 5, 1>(args, numSms, stream);
     default: return cudaErrorInvalidValue;
     }
   }
@@ -1144,6 +1155,15 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
   case 43: return launchKeyedConfig<128, 5, 3>(args, numSms, stream);
   case 54: return launchKeyedConfig<192, 3, 4>(args, numSms, stream);
   case 44: return launchKeyedConfig<128, 5, 4>(args, numSms, stream);
+  case 5: return launchKeyedConfig<256, 2, 5>(args, numSms, stream);
+  case 6: return launchKeyedConfig<256, 2, 6>(args, numSms, stream);
+  case 25: return launchKeyedConfig<256, 3, 5>(args, numSms, stream);
+  case 26: return launchKeyedConfig<256, 3, 6>(args, numSms, stream);
+  case 35: return launchKeyedConfig<192, 4, 5>(args, numSms, stream);
+  case 45: return launchKeyedConfig<128, 5, 5>(args, numSms, stream);
+  case 55: return launchKeyedConfig<192, 3, 5>(args, numSms, stream);
+  case 46: return launchKeyedConfig<128, 5, 6>(args, numSms, stream);
+  case 56: return launchKeyedConfig<192, 3, 6>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
 }

@@ -444,8 +444,11 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
   const bool fpWay = opt.rngMode == PTB200_RNG_MT19937_PER_PIXEL;
   int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable);
   if (fpWay) { // instantiated for the default configurations and the FP64 fallback only
-    const int sweep = keyedConfig % 10;
-    keyedConfig = sweep <= 1 ? 1 : sweep == 4 ? (keyedConfig / 10 == 2 ? 24 : 4) : 3;
+    const int sweep = keyedConfig % 10, shape = keyedConfig / 10;
+    if (sweep == 5)
+      keyedConfig = shape == 2 ? 25 : shape == 4 ? 45 : 5;
+    else
+      keyedConfig = sweep <= 1 ? 1 : sweep == 4 ? (shape == 2 ? 24 : 4) : 3;
   }
   size_t mtThreads = 0;
   uint32_t mtLimit = 0;

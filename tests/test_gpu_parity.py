@@ -53,7 +53,8 @@ def assert_hits_equal(got, want):
 
 
 @pytest.mark.parametrize("name", SCENE_NAMES)
-@pytest.mark.parametrize("sweep", ["two-stage", "one-stage", "fp32-stage0", "fp32x2-stage0", "fp32x2-stage0-t", "warp-cooperative"])
+@pytest.mark.parametrize("sweep", ["two-stage", "one-stage", "fp32-stage0", "fp32x2-stage0", "fp32x2-stage0-t",
+                                   "fp32x2-signs-t", "fp32x2-signs", "warp-cooperative"])
 def test_intersect_matches_oracle(name, sweep, scenes, oracle, capi):
     """Every sweep implementation (two-stage FP64 prefilter + exact, plain one-stage, FP32 stage 0 +
     exact, the sequential kernel's lane-strided sweep) returns the oracle's nearest hit bit for bit."""
@@ -62,7 +63,8 @@ def test_intersect_matches_oracle(name, sweep, scenes, oracle, capi):
     want = oracle.OracleScene(scene).intersect(rays)
     variant = {"two-stage": capi.SWEEP_TWO_STAGE_FP64, "one-stage": capi.SWEEP_ONE_STAGE,
                "fp32-stage0": capi.SWEEP_FP32_STAGE0, "fp32x2-stage0": capi.SWEEP_FP32X2_STAGE0,
-               "fp32x2-stage0-t": capi.SWEEP_FP32X2_STAGE0_T}.get(sweep)
+               "fp32x2-stage0-t": capi.SWEEP_FP32X2_STAGE0_T, "fp32x2-signs-t": capi.SWEEP_FP32X2_SIGNS_T,
+               "fp32x2-signs": capi.SWEEP_FP32X2_SIGNS}.get(sweep)
     got = capi.intersect(scene, rays, warp_cooperative=sweep == "warp-cooperative", sweep=variant)
     assert (want[:, 0] != 0).sum() > 100
     assert_hits_equal(got, want)
@@ -230,7 +232,8 @@ def test_progress_callback_runs_on_calling_thread_with_partial_frames(scenes, ca
     assert np.array_equal(final["sum"], ref["sum"])
 
 
-def test_every_megakernel_configuration_renders_identically(scenes, tmp_path):
+@pytest.mark.parametrize("scene_name,w,h", [("suzanne", 96, 72), ("cornell", 128, 96)])
+def test_every_megakernel_configuration_renders_identically(scene_name, w, h, scenes, tmp_path):
     """Every megakernel instantiation (sweep variant x launch shape, PTB200_KEYED_CONFIG) must give
     the same framebuffer and cast count bit for bit."""
     import os
@@ -240,11 +243,11 @@ def test_every_megakernel_configuration_renders_identically(scenes, tmp_path):
     code = ("import sys, numpy as np; sys.path.insert(0, %r)\n"
             "from pt_three_ways_b200 import capi, scenefile\n"
             "s = scenefile.load(%r)\n"
-            "px, st = capi.render(s, s.camera(96, 72), capi.make_params(96, 72, spp=4, seed=11))\n"
+            "px, st = capi.render(s, s.camera(%d, %d), capi.make_params(%d, %d, spp=4, seed=11))\n"
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
-                root, os.path.join(root, "tests/golden/scenes/suzanne.ptscene"))
+                root, os.path.join(root, "tests/golden/scenes/%s.ptscene" % scene_name), w, h, w, h)
     outs = []
-    for config in ("1", "0", "2", "3", "4", "13", "24", "43"):
+    for config in ("1", "0", "2", "3", "4", "13", "24", "43", "5", "6", "25", "26", "35"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
@@ -303,7 +306,8 @@ def test_random_scene_intersections_match_oracle(seed, oracle, capi):
     rays = random_scenes.rays_for(scene, 4000, seed + 20)
     want = oracle.OracleScene(scene).intersect(rays)
     for sweep in (capi.SWEEP_ONE_STAGE, capi.SWEEP_TWO_STAGE_FP64, capi.SWEEP_FP32_STAGE0,
-                  capi.SWEEP_FP32X2_STAGE0, capi.SWEEP_FP32X2_STAGE0_T):
+                  capi.SWEEP_FP32X2_STAGE0, capi.SWEEP_FP32X2_STAGE0_T, capi.SWEEP_FP32X2_SIGNS_T,
+                  capi.SWEEP_FP32X2_SIGNS):
         assert_hits_equal(capi.intersect(scene, rays, sweep=sweep), want)
     assert_hits_equal(capi.intersect(scene, rays, warp_cooperative=True), want)
     audit = capi.audit_stage0(scene, rays)
