@@ -372,6 +372,15 @@ def run_ours(args):
                 "parity": "bit-exact vs the oracle's fp policy, which equals fp::render of the reference "
                           "(src/fp/Render.cpp) image for image (tests/golden/fp_pass_*.npy)",
                 "note": "the reference's --way fp semantics; not the timed headline"}
+            # ... and its `oo` way: the sequential stream again with the oo estimator.
+            ost = ctx.render(scene.camera(ew, eh), capi.make_params(ew, eh, spp=SPP, seed=SEED),
+                             capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL_OO, device=local_rank))
+            line["oo_way_mode"] = {
+                "value": ost["samples"] / ost["kernel_ms"] / 1e3, "unit": UNIT,
+                "sample": f"{SCENE} {ew}x{eh} (same aspect), {SPP} passes, PTB200_RNG_MT19937_SEQUENTIAL_OO",
+                "parity": "bit-exact vs the oracle's oo policy, which equals oo::Renderer::radiance of the "
+                          "reference (src/oo/Renderer.cpp) image for image (tests/golden/oo_pass_*.npy)",
+                "note": "the reference's --way oo semantics, parallel over passes only; not the timed headline"}
             threads = os.cpu_count() or 1
             v, info = cpu_reference_step(threads)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, **info,

@@ -1107,9 +1107,10 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
 //                   5 = 4 and 6 = 3 with the stage-0 decisions kept in sign bits (stage0Reject2)
 //   launch shapes:  0 = 256 threads x 2 CTAs/SM (128 registers); 1 = 384 x 1 (168 registers);
 //                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5 (96 registers); 5 = 192 x 3
-// Default (measured on B200, profiles/): packed FP32 stage 0 everywhere it is usable; three CTAs
-// per SM for small scenes, where shading latency rather than the sweep limits the kernel.
-// PTB200_KEYED_CONFIG overrides it (tools/sweep_configs.py).
+// Default (measured on B200, profiles/r1s): the sign-bit stage 0 WITHOUT the negative-t test
+// (variant 6) everywhere the FP32 filter is usable — 165 vs 156 Msamples/s on Cornell, +5.5 % on
+// suzanne and ce; three CTAs per SM for small scenes, where shading latency rather than the sweep
+// limits the kernel.  PTB200_KEYED_CONFIG overrides it (tools/sweep_configs.py).
 int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
   static const int forced = [] {
     const char *env = getenv("PTB200_KEYED_CONFIG");
@@ -1118,7 +1119,7 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
   if (forced >= 0)
     return forced;
   const bool small = numTriangles <= 512;
-  const int sweep = filterUsable ? (small ? 4 : 3) : 1;
+  const int sweep = filterUsable ? 6 : 1;
   const int shape = small ? 2 : 0;
   return 10 * shape + sweep;
 }
@@ -1136,6 +1137,8 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
     case 5: return launchKeyedConfig<256, 2, 5, 1>(args, numSms, stream);
     case 25: return launchKeyedConfig<256, 3, 5, 1>(args, numSms, stream);
     case 45: return launchKeyedConfig<128, 5, 5, 1>(args, numSms, stream);
+    case 6: return launchKeyedConfig<256, 2, 6, 1>(args, numSms, stream);
+    case 26: return launchKeyedConfig<256, 3, 6, 1>(args, numSms, stream);
     default: return cudaErrorInvalidValue;
     }
   }

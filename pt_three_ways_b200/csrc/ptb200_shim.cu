@@ -445,7 +445,9 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
   int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable);
   if (fpWay) { // instantiated for the default configurations and the FP64 fallback only
     const int sweep = keyedConfig % 10, shape = keyedConfig / 10;
-    if (sweep == 5)
+    if (sweep == 6)
+      keyedConfig = shape == 2 ? 26 : 6;
+    else if (sweep == 5)
       keyedConfig = shape == 2 ? 25 : shape == 4 ? 45 : 5;
     else
       keyedConfig = sweep <= 1 ? 1 : sweep == 4 ? (shape == 2 ? 24 : 4) : 3;

@@ -121,7 +121,7 @@ def test_fp_way_camera_without_aperture(oracle, capi):
 
 
 def test_fp_way_every_instantiation_renders_identically(tmp_path):
-    """The fp way is instantiated for seven megakernel configurations (ptb200_shim.cu maps every
+    """The fp way is instantiated for nine megakernel configurations (ptb200_shim.cu maps every
     PTB200_KEYED_CONFIG onto one of them)."""
     import subprocess
     import sys
@@ -134,7 +134,7 @@ def test_fp_way_every_instantiation_renders_identically(tmp_path):
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
                 root, os.path.join(root, "tests/golden/scenes/suzanne.ptscene"))
     outs = []
-    for config in ("1", "3", "4", "24", "5", "25", "45"):
+    for config in ("1", "3", "4", "24", "5", "25", "45", "6", "26"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
