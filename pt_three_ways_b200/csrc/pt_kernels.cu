@@ -1110,8 +1110,10 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
 // Default (measured on B200, profiles/r1s): the sign-bit stage 0 WITHOUT the negative-t test
 // (variant 6) everywhere the FP32 filter is usable — 165 vs 156 Msamples/s on Cornell, +5.5 % on
 // suzanne and ce; three CTAs per SM for small scenes, where shading latency rather than the sweep
-// limits the kernel.  PTB200_KEYED_CONFIG overrides it (tools/sweep_configs.py).
-int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
+// limits the kernel — except for the fp way, whose per-lane engines want the registers of two
+// CTAs per SM (125.6 vs 122.3 Msamples/s, r1t).  PTB200_KEYED_CONFIG overrides it
+// (tools/sweep_configs.py).
+int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable, int way) {
   static const int forced = [] {
     const char *env = getenv("PTB200_KEYED_CONFIG");
     return env ? atoi(env) : -1;
@@ -1120,7 +1122,7 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable) {
     return forced;
   const bool small = numTriangles <= 512;
   const int sweep = filterUsable ? 6 : 1;
-  const int shape = small ? 2 : 0;
+  const int shape = small && way == 0 ? 2 : 0;
   return 10 * shape + sweep;
 }
 

@@ -92,7 +92,7 @@ struct IntersectArgs {
 size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
                       uint32_t threadsForPrimarySlots, int way);
 size_t mtHistoryThreadsFor(int numSms);
-int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable); // 10 * launchShape + sweepVariant
+int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable, int way); // 10 * launchShape + sweepVariant
 cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream);
 cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream);
 cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream);

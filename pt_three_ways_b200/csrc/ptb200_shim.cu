@@ -442,7 +442,7 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
   passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses));
   PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
   const bool fpWay = opt.rngMode == PTB200_RNG_MT19937_PER_PIXEL;
-  int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable);
+  int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable, fpWay ? 1 : 0);
   if (fpWay) { // instantiated for the default configurations and the FP64 fallback only
     const int sweep = keyedConfig % 10, shape = keyedConfig / 10;
     if (sweep == 6)
