@@ -28,7 +28,6 @@ namespace ptb200 {
 // =============================================================================================
 // Dynamic shared memory of a sweeping CTA (offsets from the 128-byte aligned base):
 //   [0, 16)            two mbarriers
-//   [16, 20)           the CTA's cast counter (megakernel)
 //   [32, 32 + 32 S)    spheres {centre, r^2}
 //   [tileOffset, ...)  tile buffer 0, then tile buffer 1 when the scene streams (numTiles > 1)
 // Pointers are always formed as  smemBase + offset  so the compiler keeps them in the shared
@@ -54,13 +53,12 @@ __host__ __device__ inline uint32_t smemAfterTiles(uint32_t numSpheres, uint32_t
 constexpr uint32_t kPrimaryDoubles = 16;
 constexpr uint32_t kPendingDoubles = 8;   // the prefetched next sample, see the megakernel
 constexpr uint32_t kPendingDoublesFp = 9; //   ... plus its engine's two running seed words
-constexpr uint32_t kActiveDoubles = 4;    // the sample in flight: accumulated strata (3) + its output slot
 constexpr int kPrefetchBatch = 12;        // refill the prefetch slots when this many lanes' are empty
 __host__ size_t keyedSmemBytes(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles, int sweep,
                                uint32_t threadsForPrimarySlots, int way) {
   return smemAfterTiles(numSpheres, tileTris, numTiles, sweep) +
          static_cast<size_t>(threadsForPrimarySlots) *
-             (kPrimaryDoubles + (way == 1 ? kPendingDoublesFp : kPendingDoubles) + kActiveDoubles) * sizeof(double);
+             (kPrimaryDoubles + (way == 1 ? kPendingDoublesFp : kPendingDoubles)) * sizeof(double);
 }
 
 // Streams tiles cyclically (0,1,..,n-1,0,1,..) through two buffers with TMA bulk copies.
@@ -171,8 +169,6 @@ struct KeyedDraws {
 };
 
 enum LaneMode : int { kNeedWork = 0, kTracing = 1, kFinished = 2 };
-// The lane's small state lives in ONE register (`flags`): LaneMode in bits 0-1, then these.
-constexpr uint32_t kModeMask = 3u, kPendingValid = 4u, kExhausted = 8u, kPrimarySpecular = 16u;
 
 // Camera::randomRay for the keyed policy; once per ~45 casts, so out of line.
 static __device__ __noinline__ void keyedCameraRay(const DeviceCamera &camera, uint32_t key0, uint32_t pixel,
@@ -230,8 +226,6 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
 #pragma unroll 1
   for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += kBlock)
     stream.spheres()[i] = scene.spheres[i];
-  if (threadIdx.x == 0)
-    *reinterpret_cast<unsigned *>(smemRaw + 16) = 0u;
   __syncthreads();
   const bool resident = scene.numTiles <= 1;
   if (resident && scene.numTiles == 1)
@@ -243,10 +237,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
   const V3 environment = mk(scene.environment[0], scene.environment[1], scene.environment[2]);
 
   // ---- per-lane path state ----
-  uint32_t flags = kNeedWork; // mode | kPendingValid | kExhausted | kPrimarySpecular
-  // Casts are counted per CTA in shared memory (one warp-aggregated atomic per iteration): a
-  // per-lane counter is one more register that lives across the sweep.
-  unsigned *const ctaCasts = reinterpret_cast<unsigned *>(smemRaw + 16);
+  int mode = kNeedWork;
+  uint32_t casts = 0;            // per lane and launch: far below 2^32
+  uint64_t sampleSlot = 0;       // where this sample's colour goes
   uint32_t pixel = 0;            // x + y*width (RNG key and framebuffer index)
   uint32_t key0 = 0;
   V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
@@ -256,17 +249,12 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
                                                                                   scene.numTiles, kSweep)) + threadIdx.x;
   // ... and so does this lane's prefetched next sample (6 doubles of ray + slot + key/pixel).
   double *const pendingSlot = primarySlot + kPrimaryDoubles * kBlock;
-  // ... and the sums over the strata done so far plus the index of the sample's output slot: read
-  // and written once per sub-path, so they need not occupy eight registers during the sweep.
-  double *const activeSlot = pendingSlot + (kFp ? kPendingDoublesFp : kPendingDoubles) * kBlock;
+  bool pendingValid = false, exhausted = false;
   uint32_t primaryMaterial = 0;
+  bool primarySpecular = false;
   int subPath = 0;
+  V3 acc = mk(0, 0, 0);
   // levels 1.. of the current sub-path: material index and branch taken
-  // Up to four levels (maxDepth <= 6, the reference default is 5) sit in registers: 16-bit
-  // material indices in `packedMaterials`, the branch bits in `flags` from bit 9 on; deeper paths
-  // use the local-memory arrays.  (The arrays cost two dependent local loads per unwound level.)
-  const bool packedStack = args.maxDepth <= 6;
-  unsigned long long packedMaterials = 0;
   uint16_t stackMaterial[kMaxDepth];
   bool stackSpecular[kMaxDepth];
   // fp way: this lane's engine, and the words it has generated (its slice of the scratch buffer).
@@ -281,9 +269,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
     // A camera ray costs ~400 instructions whether 1 or 32 lanes need one.  So every lane keeps
     // ONE prefetched sample (ticket + camera ray) parked in shared memory; slots are refilled
     // together once kPrefetchBatch of them are empty (or a lane is out of work right now).
-    const bool slotEmpty = (flags & (kPendingValid | kExhausted)) == 0;
+    const bool slotEmpty = !pendingValid && !exhausted;
     const unsigned emptyMask = __ballot_sync(kFullMask, slotEmpty);
-    const unsigned starvingMask = __ballot_sync(kFullMask, slotEmpty && (flags & kModeMask) == kNeedWork);
+    const unsigned starvingMask = __ballot_sync(kFullMask, slotEmpty && mode == kNeedWork);
     if (emptyMask && (starvingMask || __popc(emptyMask) >= kPrefetchBatch)) {
       unsigned long long base = 0;
       const int leader = __ffs(emptyMask) - 1;
@@ -321,19 +309,19 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
             pendingSlot[5 * kBlock] = d.z;
             pendingSlot[6 * kBlock] = __longlong_as_double(static_cast<long long>(item));
             pendingSlot[7 * kBlock] = __hiloint2double(static_cast<int>(nextKey), static_cast<int>(nextPixel));
-            flags |= kPendingValid;
+            pendingValid = true;
           }
         } else {
-          flags |= kExhausted;
+          exhausted = true;
         }
       }
     }
     __syncwarp();
-    if ((flags & kModeMask) == kNeedWork) {
-      if (flags & kPendingValid) { // start the prefetched sample
+    if (mode == kNeedWork) {
+      if (pendingValid) { // start the prefetched sample
         origin = mk(pendingSlot[0 * kBlock], pendingSlot[1 * kBlock], pendingSlot[2 * kBlock]);
         direction = mk(pendingSlot[3 * kBlock], pendingSlot[4 * kBlock], pendingSlot[5 * kBlock]);
-        activeSlot[3 * kBlock] = pendingSlot[6 * kBlock]; // the output slot, as stored
+        sampleSlot = static_cast<uint64_t>(__double_as_longlong(pendingSlot[6 * kBlock]));
         const double packed = pendingSlot[7 * kBlock];
         key0 = static_cast<uint32_t>(__double2hiint(packed));
         pixel = static_cast<uint32_t>(__double2loint(packed));
@@ -346,27 +334,26 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
           for (uint32_t i = 0; i < kMtPrefetchWords; ++i)
             history[i] = history[kMtWords + i];
         }
-        flags = (flags & ~(kModeMask | kPendingValid)) | kTracing;
+        pendingValid = false;
         depth = 0;
-      } else if (flags & kExhausted) {
-        flags = (flags & ~kModeMask) | kFinished;
+        mode = kTracing;
+      } else if (exhausted) {
+        mode = kFinished;
       }
     }
-    const bool tracing = (flags & kModeMask) == kTracing;
+    const bool tracing = mode == kTracing;
     if (resident) {
-      if (__all_sync(kFullMask, (flags & kModeMask) == kFinished))
+      if (__all_sync(kFullMask, mode == kFinished))
         break;
     } else {
-      if (__syncthreads_and((flags & kModeMask) == kFinished))
+      if (__syncthreads_and(mode == kFinished))
         break;
     }
 
     // ---- 2. cast: spheres first, then every triangle (Scene.cpp:115-122); ONE sweep site ----
     Nearest best{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim};
-    const unsigned tracingMask = __ballot_sync(kFullMask, tracing);
-    if (lane == 0 && tracingMask)
-      atomicAdd(ctaCasts, static_cast<unsigned>(__popc(tracingMask)));
     if (tracing) {
+      ++casts;
       sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), origin, direction, best);
     }
     for (uint32_t j = 0; j < scene.numTiles; ++j) {
@@ -432,9 +419,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         for (uint32_t c = 0; c < kPrimaryDoubles; ++c)
           primarySlot[c * kBlock] = values[c];
         primaryMaterial = surface.material;
-        activeSlot[0 * kBlock] = 0.0;
-        activeSlot[1 * kBlock] = 0.0;
-        activeSlot[2 * kBlock] = 0.0;
+        acc = mk(0, 0, 0);
         subPath = 0;
       }
       bounce = true;
@@ -446,7 +431,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
       V3 colour = incoming;
       if (depth == 0) {
         if (terminalPrimary && !kFp) { // maxDepth == 1: numSub children, each Vec3()
-          V3 acc = mk(0, 0, 0);
+          acc = mk(0, 0, 0);
 #pragma unroll 1
           for (int k = 0; k < numSub; ++k)
             acc = add(acc, incoming);
@@ -458,21 +443,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         // primary hit's own term, in the reference's summation order
 #pragma unroll 1
         for (int level = depth - 1; level >= 1; --level) {
-          const uint32_t levelMaterial =
-              packedStack ? static_cast<uint32_t>(packedMaterials >> (16 * (level - 1))) & 0xffffu
-                          : static_cast<uint32_t>(stackMaterial[level]);
-          const bool levelSpecular = packedStack ? ((flags >> (8 + level)) & 1u) != 0 : stackSpecular[level];
-          const MaterialView mat = materialOf(scene, levelMaterial);
-          incoming = kFp ? fpLevelRadiance(mat, fpSubSampleTerm(mat, levelSpecular, incoming), 1.0)
-                         : shadeTerm(mat, levelSpecular, incoming);
+          const MaterialView mat = materialOf(scene, stackMaterial[level]);
+          incoming = kFp ? fpLevelRadiance(mat, fpSubSampleTerm(mat, stackSpecular[level], incoming), 1.0)
+                         : shadeTerm(mat, stackSpecular[level], incoming);
         }
         const MaterialView primaryMat = materialOf(scene, primaryMaterial);
-        const V3 acc = add(mk(activeSlot[0 * kBlock], activeSlot[1 * kBlock], activeSlot[2 * kBlock]),
-                           kFp ? fpSubSampleTerm(primaryMat, (flags & kPrimarySpecular) != 0, incoming)
-                               : shadeTerm(primaryMat, (flags & kPrimarySpecular) != 0, incoming));
-        activeSlot[0 * kBlock] = acc.x;
-        activeSlot[1 * kBlock] = acc.y;
-        activeSlot[2 * kBlock] = acc.z;
+        acc = add(acc, kFp ? fpSubSampleTerm(primaryMat, primarySpecular, incoming)
+                           : shadeTerm(primaryMat, primarySpecular, incoming));
         ++subPath;
         if (subPath >= numSub) {
           colour = kFp ? fpLevelRadiance(primaryMat, acc, invNumSub) // src/fp/Render.cpp:118
@@ -484,11 +461,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         }
       }
       if (sampleDone) {
-        const uint64_t sampleSlot = static_cast<uint64_t>(__double_as_longlong(activeSlot[3 * kBlock]));
         args.samples[3 * sampleSlot + 0] = colour.x;
         args.samples[3 * sampleSlot + 1] = colour.y;
         args.samples[3 * sampleSlot + 2] = colour.z;
-        flags &= ~kModeMask; // kNeedWork
+        mode = kNeedWork;
       }
     }
     __syncwarp();
@@ -548,12 +524,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
         newDirection = normalised(transform(frame, mk(cosT * radius, sinT * radius, zScale)));
       }
       if (fromPrimary) {
-        flags = specular ? (flags | kPrimarySpecular) : (flags & ~kPrimarySpecular);
-      } else if (packedStack) {
-        const int shift = 16 * (depth - 1);
-        packedMaterials = (packedMaterials & ~(0xffffull << shift)) |
-                          (static_cast<unsigned long long>(surface.material & 0xffffu) << shift);
-        flags = (flags & ~(1u << (8 + depth))) | ((specular ? 1u : 0u) << (8 + depth));
+        primarySpecular = specular;
       } else {
         stackMaterial[depth] = static_cast<uint16_t>(surface.material);
         stackSpecular[depth] = specular;
@@ -567,10 +538,13 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
 
   if (!resident)
     stream.drain();
-  // one global atomic per CTA for the cast counter
-  __syncthreads();
-  if (threadIdx.x == 0 && *ctaCasts)
-    atomicAdd(args.castCounter, static_cast<unsigned long long>(*ctaCasts));
+  // one atomic per warp for the cast counter
+  unsigned long long warpCasts = casts;
+#pragma unroll 1
+  for (int offset = 16; offset > 0; offset >>= 1)
+    warpCasts += __shfl_down_sync(kFullMask, warpCasts, offset);
+  if (lane == 0 && warpCasts)
+    atomicAdd(args.castCounter, warpCasts);
 }
 
 // =============================================================================================

@@ -50,7 +50,7 @@ int fail(int code, const char *format, ...) {
 // Budget: two CTAs per SM must fit in 227 KB, each with its tile buffer(s) plus 48 KB of
 // per-thread slots (primary hit + prefetched sample, 192 B x 256 threads).
 constexpr size_t kResidentTileBytes = 72 * 1024; // <= 1024 triangles: one resident tile per CTA
-constexpr size_t kStreamTileBytes = 36 * 1024;   // larger scenes: two buffers of <= 512 triangles
+constexpr size_t kStreamTileBytes = 40 * 1024;   // larger scenes: two buffers of <= 568 triangles
 constexpr size_t kSampleBufferBytes = size_t(4) << 30;
 
 // ---- host restatement of the per-triangle values the reference derives in addTriangle ----
