@@ -106,6 +106,8 @@ RENDER_CASES = [
     ("cornell", 33, 17, 2, 5, dict(first_u=2, first_v=3, max_depth=3)),
     ("cornell", 24, 18, 2, 9, dict(max_depth=1)),
     ("cornell", 24, 18, 1, 9, dict(preview=1)),
+    ("cornell", 20, 15, 2, 4, dict(max_depth=6)),   # deeper than the reference default
+    ("cornell", 20, 15, 2, 4, dict(max_depth=7)),   
     ("suzanne", 32, 24, 2, 2, {}),
     ("single-sphere", 32, 24, 2, 3, {}),
     ("multi-sphere", 32, 24, 2, 4, {}),
@@ -116,7 +118,7 @@ RENDER_CASES = [
 
 
 @pytest.mark.parametrize("mode_name", ["keyed", "sequential"])
-@pytest.mark.parametrize("case", RENDER_CASES, ids=lambda c: f"{c[0]}-{c[1]}x{c[2]}-{c[3]}spp")
+@pytest.mark.parametrize("case", RENDER_CASES, ids=lambda c: f"{c[0]}-{c[1]}x{c[2]}-{c[3]}spp-{len(c[5])}{c[5].get('max_depth', '')}")
 def test_render_matches_oracle(case, mode_name, scenes, oracle, capi):
     name, w, h, spp, seed, kw = case
     mode = capi.RNG_KEYED_PHILOX if mode_name == "keyed" else capi.RNG_MT19937_SEQUENTIAL
