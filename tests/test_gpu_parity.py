@@ -234,7 +234,7 @@ def test_progress_callback_runs_on_calling_thread_with_partial_frames(scenes, ca
     assert np.array_equal(final["sum"], ref["sum"])
 
 
-@pytest.mark.parametrize("scene_name,w,h", [("suzanne", 96, 72), ("cornell", 128, 96)])
+@pytest.mark.parametrize("scene_name,w,h", [("suzanne", 96, 72), ("cornell", 128, 96), ("ce", 16, 9)])
 def test_every_megakernel_configuration_renders_identically(scene_name, w, h, scenes, tmp_path):
     """Every megakernel instantiation (sweep variant x launch shape, PTB200_KEYED_CONFIG) must give
     the same framebuffer and cast count bit for bit."""
@@ -249,7 +249,7 @@ def test_every_megakernel_configuration_renders_identically(scene_name, w, h, sc
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
                 root, os.path.join(root, "tests/golden/scenes/%s.ptscene" % scene_name), w, h, w, h)
     outs = []
-    for config in ("1", "0", "2", "3", "4", "13", "24", "43", "5", "6", "25", "26", "35"):
+    for config in ("1", "0", "2", "3", "4", "13", "24", "43", "5", "6", "25", "26", "35", "46", "56", "66", "76"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
