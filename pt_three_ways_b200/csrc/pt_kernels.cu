@@ -1106,9 +1106,10 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
 //                   rejects triangles certainly behind the ray (pays off on small scenes);
 //                   5 = 4 and 6 = 3 with the stage-0 decisions kept in sign bits (stage0Reject2)
 //   launch shapes:  0 = 256 threads x 2 CTAs/SM (128 registers); 1 = 384 x 1 (168 registers);
-//                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5 (96 registers); 5 = 192 x 3;
-//                   6 = 640 x 1 (96 registers) and 7 = 768 x 1 (80): one big CTA per SM for scenes
-//                   whose tile leaves room for only two 256-thread CTAs
+//                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5 (96 registers); 5 = 192 x 3
+//                   (one big CTA per SM, 640 x 1 / 768 x 1, was measured for the scenes whose tile
+//                   leaves room for only two 256-thread CTAs: no gain on suzanne, -18 % / -29 % on ce
+//                   where every tile hand-over is a CTA-wide barrier; profiles/sweep_*_r1v.jsonl)
 // Default (measured on B200, profiles/r1s): the sign-bit stage 0 WITHOUT the negative-t test
 // (variant 6) everywhere the FP32 filter is usable — 165 vs 156 Msamples/s on Cornell, +5.5 % on
 // suzanne and ce; three CTAs per SM for small scenes, where shading latency rather than the sweep
@@ -1171,8 +1172,6 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
   case 55: return launchKeyedConfig<192, 3, 5>(args, numSms, stream);
   case 46: return launchKeyedConfig<128, 5, 6>(args, numSms, stream);
   case 56: return launchKeyedConfig<192, 3, 6>(args, numSms, stream);
-  case 66: return launchKeyedConfig<640, 1, 6>(args, numSms, stream);
-  case 76: return launchKeyedConfig<768, 1, 6>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
 }
