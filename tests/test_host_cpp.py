@@ -5,6 +5,8 @@ SceneBuilder adaptor, and the no-CPU-fallback behaviour of render()."""
 import os
 import subprocess
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "pt_three_ways_b200", "host")
 
@@ -32,6 +34,25 @@ def test_cli_rejects_bad_arguments():
     res = subprocess.run([exe, "--scene", "nonesuch", "--scenes", "/nonexistent", "out.png"],
                          capture_output=True, text=True)
     assert res.returncode == 1 and "Unknown scene" in res.stderr
+
+
+def test_cli_accepts_every_way_and_has_no_cpu_fallback(tmp_path):
+    """--way dod|fp|oo are all accepted (main.cpp:345-366); without a CUDA device the render fails
+    loudly instead of falling back to a CPU path."""
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "pt_three_ways_b200", "libptb200.so"))
+    count = ctypes.c_int32(0)
+    lib.ptb200_device_count(ctypes.byref(count))
+    if count.value > 0:
+        pytest.skip("a CUDA device is present")
+    exe = os.path.join(HOST, "pt_b200")
+    scene = os.path.join(ROOT, "tests", "golden", "scenes", "cornell.ptscene")
+    for way in ("dod", "fp", "oo"):
+        res = subprocess.run([exe, "--way", way, "--ptscene", scene, "--raw", "-w", "8", "-h", "6", "--spp", "1",
+                              "--seed", "1", str(tmp_path / "out.raw")], capture_output=True, text=True)
+        assert res.returncode == 1 and "no CPU fallback" in res.stderr, res.stderr
+        assert "38 triangles and 1 spheres" in res.stdout
+        assert not (tmp_path / "out.raw").exists()
 
 
 def test_raw_to_png_merges_like_the_reference_tool(tmp_path):
