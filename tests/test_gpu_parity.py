@@ -271,10 +271,11 @@ def test_cpp_host_adaptor_and_cli_render_identically(scenes, capi, tmp_path):
     if not os.path.exists(exe):
         subprocess.run(["make", "-C", host], check=True, capture_output=True)
     fixture = os.path.join(root, "tests", "golden", "scenes", "cornell.ptscene")
-    for rng, mode in (("keyed", capi.RNG_KEYED_PHILOX), ("exact", capi.RNG_MT19937_SEQUENTIAL)):
-        out = str(tmp_path / f"cli_{rng}.raw")
+    for flags, mode in ((("--rng", "keyed"), capi.RNG_KEYED_PHILOX), (("--rng", "exact"), capi.RNG_MT19937_SEQUENTIAL),
+                        (("--way", "fp"), capi.RNG_MT19937_PER_PIXEL), (("--way", "oo"), capi.RNG_MT19937_SEQUENTIAL_OO)):
+        out = str(tmp_path / f"cli_{flags[1]}.raw")
         res = subprocess.run([exe, "--ptscene", fixture, "-w", "48", "-h", "36", "--spp", "3", "--seed", "7",
-                              "--save-every", "0", "--rng", rng, "--raw", out],
+                              "--save-every", "0", *flags, "--raw", out],
                              capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stderr
         assert "Scene contains 38 triangles and 1 spheres." in res.stdout
