@@ -41,6 +41,29 @@ struct KeyedArgs {
   unsigned long long *castCounter;
 };
 
+// The keyed policy as a pipeline (pt_split.cu): camera rays + first hits, sub-paths, resolve.
+struct SplitArgs {
+  DeviceScene scene;
+  DeviceCamera camera;
+  uint32_t width, height;
+  int32_t rowBegin, rowStep;
+  uint32_t ownPixels;              // pixels of the selected rows
+  uint32_t totalSamples;           // ownPixels * passes of this batch; totalSamples * numSub < 2^32
+  uint32_t numPasses;              // passes of this batch
+  uint32_t numSub;                 // firstBounceU * firstBounceV
+  uint32_t numMaterials;
+  int32_t seed, passBegin;         // pass s of the batch uses key seed + passBegin + s
+  int32_t maxDepth, firstBounceU, firstBounceV, preview;
+  int32_t firstBounceUPow2, firstBounceVPow2; // strata counts are powers of two:
+  double invFirstBounceU, invFirstBounceV;    //   divide by multiplying with the exact reciprocal
+  double2 *records;                // [<= totalSamples][9]: what radiance() holds at a camera ray's hit
+  double *terms;                   // [totalSamples][numSub][3]: one term per stratum (or, for a sample
+                                   //   that ended at the camera ray, its colour in the first slot)
+  uint8_t *sampleKind;             // [totalSamples] 0: strata terms, 1: colour
+  unsigned long long *counters;    // [0] sub-path ticket, [1] casts, [2] records appended
+  PtPixelDevice *accumulator;      // full frame
+};
+
 struct SequentialArgs {
   DeviceScene scene;
   DeviceCamera camera;
@@ -96,6 +119,8 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable, int way); // 10 
 cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream);
 cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream);
 cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream);
+size_t splitBytesPerSample(uint32_t numSub);
+cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cudaStream_t stream); // 3 launches
 cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream);
 cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream);
 cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream);

@@ -1,0 +1,520 @@
+// The keyed policy as a three-kernel pipeline (the default since round 2; the one-kernel
+// megakernel of pt_kernels.cu remains for the `fp` way, whose engine is sequential within a sample).
+//
+//   primaryHitsKernel     one lane per (pass, pixel) SAMPLE: Camera::randomRay, the first
+//                         Scene::intersect, and everything radiance() holds at depth 0 when it
+//                         enters its sampling loop (Scene.cpp:124-152) written as a 144-byte record.
+//                         Samples that end at the camera ray (miss, preview, maxDepth <= 1) get
+//                         their colour directly.
+//   subPathKernel         persistent, one lane per SUB-PATH = (record, stratum): the loop body of
+//                         Scene.cpp:155-175 for one (uSample, vSample) with the recursion below it.
+//                         Every lane of every iteration does the same three things — bounce, cast,
+//                         then shade the hit or unwind and take the next ticket — so there is no
+//                         camera ray, no stratum bookkeeping and no sample completion inside the hot
+//                         loop (the one-kernel form spent half of its instructions there at 7-28
+//                         active lanes, profiles/r1t_hotspots.md).
+//   resolveSamplesKernel  per pixel: the strata's terms added in stratum order and averaged
+//                         (Scene.cpp:168,172-174,178), samples added to the accumulator in pass
+//                         order (SampledPixel.cpp:3-6).
+//
+// Results are bit-identical to the one-kernel form (and to the oracle): the same arithmetic in
+// the same order, only distributed differently over lanes.
+#include "pt_kernels.h"
+
+#include "pt_device.cuh"
+#include "pt_stage.cuh"
+
+namespace ptb200 {
+
+// ---- the record of a camera ray's hit: 9 x 16 bytes ------------------------------------------
+//   q0 pos.x pos.y | q1 pos.z nrm.x | q2 nrm.y nrm.z | q3 inc.x inc.y | q4 inc.z bX.x
+//   q5 bX.y bX.z   | q6 bY.x bY.y   | q7 bY.z reflectivity
+//   q8 {material | pixel << 32} {key0 | sample << 32}
+constexpr int kRecordQuads = 9;
+
+__device__ __forceinline__ double packWords(uint32_t lo, uint32_t hi) {
+  return __hiloint2double(static_cast<int>(hi), static_cast<int>(lo));
+}
+__device__ __forceinline__ uint32_t lowWord(double v) { return static_cast<uint32_t>(__double2loint(v)); }
+__device__ __forceinline__ uint32_t highWord(double v) { return static_cast<uint32_t>(__double2hiint(v)); }
+
+__device__ __forceinline__ void storeRecord(double2 *record, const Surface &s, uint32_t pixel, uint32_t key0,
+                                            uint32_t sample) {
+  record[0] = make_double2(s.position.x, s.position.y);
+  record[1] = make_double2(s.position.z, s.normal.x);
+  record[2] = make_double2(s.normal.y, s.normal.z);
+  record[3] = make_double2(s.incoming.x, s.incoming.y);
+  record[4] = make_double2(s.incoming.z, s.basisX.x);
+  record[5] = make_double2(s.basisX.y, s.basisX.z);
+  record[6] = make_double2(s.basisY.x, s.basisY.y);
+  record[7] = make_double2(s.basisY.z, s.reflectivity);
+  record[8] = make_double2(packWords(s.material, pixel), packWords(key0, sample));
+}
+
+// Material of the nearest hit without the rest of the hit epilogue: all the deepest level of a
+// path needs (its children return Vec3(), Scene.cpp:128-129, so it contributes its emission).
+__device__ __forceinline__ uint32_t hitMaterial(const DeviceScene &scene, const Nearest &best) {
+  if (best.prim < 0)
+    return __ldg(scene.sphereMaterial + (-best.prim - 1));
+  return static_cast<uint32_t>(__ldg(reinterpret_cast<const double *>(scene.triShade + 4 * static_cast<size_t>(best.prim)) + 3));
+}
+
+// Scene::intersect for one lane: spheres first, then every tile (Scene.cpp:115-122).  Whole-CTA
+// when the scene streams (every thread takes part in the tile hand-over).
+template <int kSweep>
+__device__ __forceinline__ Nearest castRay(const DeviceScene &scene, TileStream &stream, bool resident, bool tracing,
+                                           V3 origin, V3 direction) {
+  Nearest best{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim};
+  if (tracing)
+    sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), origin, direction, best);
+  for (uint32_t j = 0; j < scene.numTiles; ++j) {
+    const unsigned char *tile = resident ? stream.tile(0) : stream.acquire();
+    if (tracing)
+      sweepStagedTile<kSweep, false>(scene, tile, j, origin, direction, best);
+    if (!resident)
+      stream.release();
+  }
+  return best;
+}
+
+// The Surface of a hit a bounce will leave from (Scene.cpp:135-152).
+__device__ __forceinline__ Surface surfaceOfHit(const DeviceScene &scene, const double4 *spheres, V3 origin,
+                                                V3 direction, const Nearest &best) {
+  const HitInfo hit = finishHit(scene, spheres, origin, direction, best);
+  Surface surface;
+  surface.position = hit.position;
+  surface.normal = hit.normal;
+  surface.incoming = direction;
+  surface.material = hit.material;
+  surface.reflectivity = hitReflectivity(materialOf(scene, hit.material), hit, direction);
+  hitBasis(scene, hit, surface.basisX, surface.basisY);
+  return surface;
+}
+
+// =============================================================================================
+// 1. Camera rays and their hits.
+// =============================================================================================
+template <int kBlock, int kSweep>
+__global__ void __launch_bounds__(kBlock) primaryHitsKernel(const __grid_constant__ SplitArgs args) {
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  const DeviceScene &scene = args.scene;
+  TileStream stream = makeTileStream(smemRaw, scene, kSweep);
+  stream.start();
+#pragma unroll 1
+  for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += kBlock)
+    stream.spheres()[i] = scene.spheres[i];
+  __syncthreads();
+  const bool resident = scene.numTiles <= 1;
+  if (resident && scene.numTiles == 1)
+    stream.acquire();
+
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t numSub = args.numSub;
+  const double invNumSub = 1.0 / static_cast<double>(numSub); // Vec3::operator/ (Vec3.h:51-54)
+  unsigned long long casts = 0;
+  const uint32_t numChunks = (args.totalSamples + kBlock - 1) / kBlock;
+  for (uint32_t chunk = blockIdx.x; chunk < numChunks; chunk += gridDim.x) {
+    const uint32_t sample = chunk * kBlock + threadIdx.x;
+    const bool live = sample < args.totalSamples;
+    const uint32_t passInBatch = sample / args.ownPixels;
+    const uint32_t own = sample % args.ownPixels;
+    const int px = static_cast<int>(own % args.width);
+    const int py = args.rowBegin + static_cast<int>(own / args.width) * args.rowStep;
+    const uint32_t pixel = static_cast<uint32_t>(px) + static_cast<uint32_t>(py) * args.width;
+    const uint32_t key0 = static_cast<uint32_t>(args.seed + args.passBegin + static_cast<int>(passInBatch));
+    const bool tracing = live && args.maxDepth > 0; // radiance() returns Vec3() before intersecting (Scene.cpp:128-129)
+    V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
+    if (tracing)
+      keyedCameraRay(args.camera, key0, pixel, px, py, origin, direction);
+    const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, origin, direction);
+    casts += tracing ? 1u : 0u;
+
+    bool isRecord = false;
+    V3 colour = mk(0, 0, 0);
+    Surface surface{};
+    if (tracing) {
+      if (best.prim == kNoPrim) {
+        colour = mk(scene.environment[0], scene.environment[1], scene.environment[2]); // Scene.cpp:132-133
+      } else if (args.preview) { // Scene.cpp:137-138
+        colour = materialOf(scene, hitMaterial(scene, best)).diffuse();
+      } else if (args.maxDepth <= 1) {
+        // The sampling loop still runs, every child returns Vec3(): numSub emission terms, averaged.
+        const V3 term = shadeTerm(materialOf(scene, hitMaterial(scene, best)), true, mk(0, 0, 0));
+        V3 acc = mk(0, 0, 0);
+#pragma unroll 1
+        for (uint32_t k = 0; k < numSub; ++k)
+          acc = add(acc, term);
+        colour = scale(acc, invNumSub);
+      } else {
+        surface = surfaceOfHit(scene, stream.spheres(), origin, direction, best);
+        isRecord = true;
+      }
+    }
+    // Records are appended in whatever order warps arrive: results are addressed by sample.
+    const unsigned recordMask = __ballot_sync(kFullMask, isRecord);
+    if (recordMask) {
+      unsigned long long base = 0;
+      const int leader = __ffs(recordMask) - 1;
+      if (static_cast<int>(lane) == leader)
+        base = atomicAdd(args.counters + 2, static_cast<unsigned long long>(__popc(recordMask)));
+      base = __shfl_sync(kFullMask, base, leader);
+      if (isRecord) {
+        const unsigned long long index = base + __popc(recordMask & ((1u << lane) - 1u));
+        storeRecord(args.records + kRecordQuads * index, surface, pixel, key0, sample);
+        args.sampleKind[sample] = 0;
+      }
+    }
+    if (live && !isRecord) {
+      double *slot = args.terms + 3 * static_cast<size_t>(sample) * numSub;
+      slot[0] = colour.x;
+      slot[1] = colour.y;
+      slot[2] = colour.z;
+      args.sampleKind[sample] = 1;
+    }
+  }
+  if (!resident)
+    stream.drain();
+#pragma unroll 1
+  for (int offset = 16; offset > 0; offset >>= 1)
+    casts += __shfl_down_sync(kFullMask, casts, offset);
+  if (lane == 0 && casts)
+    atomicAdd(args.counters + 1, casts);
+}
+
+// =============================================================================================
+// 2. Sub-paths.
+// =============================================================================================
+constexpr unsigned long long kTicketGrab = 64; // tickets a warp takes per atomic (>= 32)
+
+// Levels 1.. of a sub-path: material index and branch taken, for the unwind.  Paths of the
+// reference's default depth keep them in one 64-bit register (16 bits per level); deeper ones in
+// local memory.
+template <bool kDeep>
+struct LevelStack;
+template <>
+struct LevelStack<false> {
+  static constexpr int kLevels = 4;
+  unsigned long long bits;
+  __device__ __forceinline__ void reset() { bits = 0; }
+  __device__ __forceinline__ void set(int level, uint32_t material, bool specular) { // level >= 1, once per path
+    bits |= static_cast<unsigned long long>(material | (specular ? 0x8000u : 0u)) << (16 * (level - 1));
+  }
+  __device__ __forceinline__ void get(int level, uint32_t &material, bool &specular) const {
+    const uint32_t entry = static_cast<uint32_t>(bits >> (16 * (level - 1)));
+    material = entry & 0x7fffu;
+    specular = (entry & 0x8000u) != 0;
+  }
+};
+template <>
+struct LevelStack<true> {
+  uint16_t material_[kMaxDepth];
+  bool specular_[kMaxDepth];
+  __device__ __forceinline__ void reset() {}
+  __device__ __forceinline__ void set(int level, uint32_t material, bool specular) {
+    material_[level] = static_cast<uint16_t>(material);
+    specular_[level] = specular;
+  }
+  __device__ __forceinline__ void get(int level, uint32_t &material, bool &specular) const {
+    material = material_[level];
+    specular = specular_[level];
+  }
+};
+
+template <int kBlock, int kMinBlocks, int kSweep, bool kDeep>
+__global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid_constant__ SplitArgs args) {
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  const DeviceScene &scene = args.scene;
+  TileStream stream = makeTileStream(smemRaw, scene, kSweep);
+  stream.start();
+#pragma unroll 1
+  for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += kBlock)
+    stream.spheres()[i] = scene.spheres[i];
+  __syncthreads();
+  const bool resident = scene.numTiles <= 1;
+  if (resident && scene.numTiles == 1)
+    stream.acquire(); // the one tile stays in buffer 0 for the whole launch
+
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t numSub = args.numSub;
+  const unsigned long long totalItems = args.counters[2] * numSub; // records the first kernel appended
+  const V3 environment = mk(scene.environment[0], scene.environment[1], scene.environment[2]);
+
+  // ---- per-lane path state ----
+  V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
+  int depth = 0;              // depth of the ray in flight (>= 1 after the first bounce)
+  uint32_t pixel = 0, key0 = 0, subPath = 0;
+  uint32_t termIndex = 0;     // sample * numSub + subPath
+  uint32_t primaryMaterial = 0;
+  bool primarySpecular = false;
+  LevelStack<kDeep> stack;
+  stack.reset();
+  Surface surface{};          // what the next bounce leaves from
+  bool needItem = true, finished = false;
+  unsigned long long poolNext = 0, poolEnd = 0; // this warp's tickets (warp-uniform)
+  unsigned long long warpCasts = 0;             // warp-uniform
+
+  for (;;) {
+    // ---- 1. the next sub-path for lanes whose path has ended ----
+    const unsigned needMask = __ballot_sync(kFullMask, needItem);
+    if (needMask) {
+      const unsigned long long want = static_cast<unsigned long long>(__popc(needMask));
+      const unsigned long long rank = static_cast<unsigned long long>(__popc(needMask & ((1u << lane) - 1u)));
+      const unsigned long long available = poolEnd - poolNext;
+      unsigned long long item;
+      if (available >= want) {
+        item = poolNext + rank;
+        poolNext += want;
+      } else { // the rest of the old pool, then a fresh one
+        unsigned long long base = 0;
+        if (lane == 0)
+          base = atomicAdd(args.counters, kTicketGrab);
+        base = __shfl_sync(kFullMask, base, 0);
+        item = rank < available ? poolNext + rank : base + (rank - available);
+        poolNext = base + (want - available);
+        poolEnd = base + kTicketGrab;
+      }
+      if (needItem) {
+        needItem = false;
+        if (item >= totalItems) {
+          finished = true;
+        } else {
+          const uint32_t recordIndex = static_cast<uint32_t>(item / numSub);
+          subPath = static_cast<uint32_t>(item) - recordIndex * numSub;
+          const double2 *record = args.records + kRecordQuads * static_cast<size_t>(recordIndex);
+          const double2 q0 = record[0], q1 = record[1], q2 = record[2], q3 = record[3], q4 = record[4],
+                        q5 = record[5], q6 = record[6], q7 = record[7], q8 = record[8];
+          surface.position = mk(q0.x, q0.y, q1.x);
+          surface.normal = mk(q1.y, q2.x, q2.y);
+          surface.incoming = mk(q3.x, q3.y, q4.x);
+          surface.basisX = mk(q4.y, q5.x, q5.y);
+          surface.basisY = mk(q6.x, q6.y, q7.x);
+          surface.reflectivity = q7.y;
+          surface.material = lowWord(q8.x);
+          pixel = highWord(q8.x);
+          key0 = lowWord(q8.y);
+          termIndex = highWord(q8.y) * numSub + subPath;
+          depth = 0;
+          stack.reset();
+        }
+      }
+    }
+    __syncwarp();
+    if (resident) {
+      if (__all_sync(kFullMask, finished))
+        break;
+    } else {
+      if (__syncthreads_and(finished))
+        break;
+    }
+    const bool tracing = !finished;
+
+    // ---- 2. bounce: one (u, v, p) triple, cone or hemisphere sample (Scene.cpp:157-175) ----
+    if (tracing) {
+      double ru, rv, rp;
+      KeyedDraws{key0}.bounce(pixel, subPath, static_cast<uint32_t>(depth), ru, rv, rp);
+      double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
+      if (depth == 0) {
+        // u-major strata (Scene.cpp:155-156); x / n == x * (1/n) exactly when n is a power of two
+        const double su = static_cast<double>(subPath / static_cast<uint32_t>(args.firstBounceV)) + ru;
+        const double sv = static_cast<double>(subPath % static_cast<uint32_t>(args.firstBounceV)) + rv;
+        u = args.firstBounceUPow2 ? su * args.invFirstBounceU : ieeeDiv(su, static_cast<double>(args.firstBounceU));
+        v = args.firstBounceVPow2 ? sv * args.invFirstBounceV : ieeeDiv(sv, static_cast<double>(args.firstBounceV));
+      }
+      // coneSample() / hemisphereSample() (Samples.cpp:6-30) end in the same
+      // normalised(basis.transform(cos(t)*r, sin(t)*r, z)): the few specular lanes only prepare
+      // its inputs, then every lane runs that tail together.
+      const bool specular = rp < surface.reflectivity;
+      Basis frame{surface.basisX, surface.basisY, surface.normal};
+      double angle = (2 * kPi) * u, radius = 0, zScale = 0;
+      bool direct = false;
+      V3 newDirection = mk(0, 0, 0);
+      if (specular) {
+        newDirection = reflect(surface.normal, surface.incoming);
+        direct = coneSampleSetup(newDirection, materialOf(scene, surface.material).coneAngle(), u, v, frame,
+                                 angle, radius, zScale);
+      } else {
+        radius = ieeeSqrt(v);
+        zScale = ieeeSqrt(1 - v);
+      }
+      if (!direct) {
+        double sinT, cosT;
+        sinCos(angle, sinT, cosT);
+        newDirection = normalised(transform(frame, mk(cosT * radius, sinT * radius, zScale)));
+      }
+      if (depth == 0) {
+        primaryMaterial = surface.material;
+        primarySpecular = specular;
+      } else {
+        stack.set(depth, surface.material, specular);
+      }
+      origin = surface.position;
+      direction = newDirection;
+      ++depth;
+    }
+    __syncwarp();
+
+    // ---- 3. cast ----
+    warpCasts += static_cast<unsigned long long>(__popc(__ballot_sync(kFullMask, tracing)));
+    const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, origin, direction);
+
+    // ---- 4. the hit becomes the next bounce's surface, or the path ends ----
+    bool ended = false;
+    V3 incoming = mk(0, 0, 0);
+    if (tracing) {
+      if (best.prim == kNoPrim) {
+        incoming = environment; // Scene.cpp:132-133
+        ended = true;
+      } else if (depth + 1 >= args.maxDepth) {
+        // Deepest level: its sampling loop runs, but every child returns Vec3() (Scene.cpp:128-129).
+        incoming = shadeTerm(materialOf(scene, hitMaterial(scene, best)), true, mk(0, 0, 0));
+        ended = true;
+      } else {
+        surface = surfaceOfHit(scene, stream.spheres(), origin, direction, best);
+      }
+    }
+    __syncwarp();
+    if (ended) {
+      // unwind levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum), then the camera
+      // hit's own term for this stratum
+#pragma unroll 1
+      for (int level = depth - 1; level >= 1; --level) {
+        uint32_t material;
+        bool specular;
+        stack.get(level, material, specular);
+        incoming = shadeTerm(materialOf(scene, material), specular, incoming);
+      }
+      const V3 term = shadeTerm(materialOf(scene, primaryMaterial), primarySpecular, incoming);
+      double *slot = args.terms + 3 * static_cast<size_t>(termIndex);
+      slot[0] = term.x;
+      slot[1] = term.y;
+      slot[2] = term.z;
+      needItem = true;
+    }
+    __syncwarp();
+  }
+
+  if (!resident)
+    stream.drain();
+  if (lane == 0 && warpCasts)
+    atomicAdd(args.counters + 1, warpCasts);
+}
+
+// =============================================================================================
+// 3. Strata -> samples -> pixels, both sums in the reference's order.
+// =============================================================================================
+__global__ void resolveSamplesKernel(const __grid_constant__ SplitArgs args) {
+  const uint32_t own = blockIdx.x * blockDim.x + threadIdx.x;
+  if (own >= args.ownPixels)
+    return;
+  const uint32_t px = own % args.width;
+  const uint32_t py = static_cast<uint32_t>(args.rowBegin) + (own / args.width) * static_cast<uint32_t>(args.rowStep);
+  PtPixelDevice *dst = args.accumulator + (px + static_cast<size_t>(py) * args.width);
+  const uint32_t numSub = args.numSub;
+  const double invNumSub = 1.0 / static_cast<double>(numSub);
+  double r = dst->sum[0], g = dst->sum[1], b = dst->sum[2];
+  for (uint32_t p = 0; p < args.numPasses; ++p) {
+    const size_t sample = static_cast<size_t>(p) * args.ownPixels + own;
+    const double *t = args.terms + 3 * sample * numSub;
+    V3 colour;
+    if (args.sampleKind[sample]) {
+      colour = mk(t[0], t[1], t[2]);
+    } else {
+      V3 acc = mk(0, 0, 0);
+      for (uint32_t k = 0; k < numSub; ++k)
+        acc = add(acc, mk(t[3 * k], t[3 * k + 1], t[3 * k + 2]));
+      colour = scale(acc, invNumSub); // Scene.cpp:178
+    }
+    r += colour.x;
+    g += colour.y;
+    b += colour.z;
+  }
+  dst->sum[0] = r;
+  dst->sum[1] = g;
+  dst->sum[2] = b;
+  dst->numSamples += args.numPasses;
+}
+
+// =============================================================================================
+// Host-side launchers.
+// =============================================================================================
+size_t splitBytesPerSample(uint32_t numSub) {
+  return kRecordQuads * sizeof(double2) + 3 * sizeof(double) * static_cast<size_t>(numSub) + 1;
+}
+
+template <int kBlock, int kSweep>
+static cudaError_t launchPrimary(const SplitArgs &args, int numSms, cudaStream_t stream) {
+  auto kernel = primaryHitsKernel<kBlock, kSweep>;
+  const size_t smemBytes = smemAfterTiles(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep);
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes));
+  if (err != cudaSuccess)
+    return err;
+  int perSm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlock, smemBytes);
+  if (err != cudaSuccess)
+    return err;
+  if (perSm < 1)
+    return cudaErrorInvalidConfiguration;
+  const unsigned long long chunks = (static_cast<unsigned long long>(args.totalSamples) + kBlock - 1) / kBlock;
+  unsigned long long grid = static_cast<unsigned long long>(numSms) * perSm;
+  if (chunks < grid)
+    grid = chunks ? chunks : 1;
+  kernel<<<static_cast<unsigned>(grid), kBlock, smemBytes, stream>>>(args);
+  return cudaGetLastError();
+}
+
+template <int kBlock, int kMinBlocks, int kSweep, bool kDeep>
+static cudaError_t launchSubPaths(const SplitArgs &args, int numSms, cudaStream_t stream) {
+  auto kernel = subPathKernel<kBlock, kMinBlocks, kSweep, kDeep>;
+  const size_t smemBytes = smemAfterTiles(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep);
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes));
+  if (err != cudaSuccess)
+    return err;
+  int perSm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlock, smemBytes);
+  if (err != cudaSuccess)
+    return err;
+  if (perSm < 1)
+    return cudaErrorInvalidConfiguration;
+  // Persistent grid: every SM holds `perSm` CTAs for the whole launch (148 x perSm on B200); the
+  // number of sub-paths is only known on the device (records x strata).
+  const unsigned long long wanted = (static_cast<unsigned long long>(args.totalSamples) * args.numSub + kBlock - 1) / kBlock;
+  unsigned long long grid = static_cast<unsigned long long>(numSms) * perSm;
+  if (wanted < grid)
+    grid = wanted ? wanted : 1;
+  kernel<<<static_cast<unsigned>(grid), kBlock, smemBytes, stream>>>(args);
+  return cudaGetLastError();
+}
+
+template <int kBlock, int kMinBlocks, int kSweep>
+static cudaError_t launchSplitShape(const SplitArgs &args, int numSms, cudaStream_t stream) {
+  cudaError_t err = launchPrimary<256, kSweep>(args, numSms, stream);
+  if (err != cudaSuccess)
+    return err;
+  const bool deep = args.maxDepth - 2 > LevelStack<false>::kLevels || args.numMaterials > 0x8000u;
+  err = deep ? launchSubPaths<kBlock, kMinBlocks, kSweep, true>(args, numSms, stream)
+             : launchSubPaths<kBlock, kMinBlocks, kSweep, false>(args, numSms, stream);
+  if (err != cudaSuccess)
+    return err;
+  const int block = 128;
+  resolveSamplesKernel<<<(args.ownPixels + block - 1) / block, block, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
+// A pipeline configuration is 100 + 10 * launchShape + sweepVariant (the megakernel's numbering
+// plus 100): sweep variants 1 (two-stage FP64) and 6 (sign-bit FP32 stage 0 + exact); launch
+// shapes of the sub-path kernel 0 = 256 threads x 2 CTAs/SM, 2 = 256 x 3, 3 = 192 x 4, 4 = 128 x 5,
+// 6 = 256 x 4.
+cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cudaStream_t stream) {
+  switch (config) {
+  case 101: return launchSplitShape<256, 2, 1>(args, numSms, stream);
+  case 106: return launchSplitShape<256, 2, 6>(args, numSms, stream);
+  case 121: return launchSplitShape<256, 3, 1>(args, numSms, stream);
+  case 126: return launchSplitShape<256, 3, 6>(args, numSms, stream);
+  case 136: return launchSplitShape<192, 4, 6>(args, numSms, stream);
+  case 146: return launchSplitShape<128, 5, 6>(args, numSms, stream);
+  case 166: return launchSplitShape<256, 4, 6>(args, numSms, stream);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+} // namespace ptb200

@@ -52,6 +52,9 @@ int fail(int code, const char *format, ...) {
 constexpr size_t kResidentTileBytes = 72 * 1024; // <= 1024 triangles: one resident tile per CTA
 constexpr size_t kStreamTileBytes = 40 * 1024;   // larger scenes: two buffers of <= 568 triangles
 constexpr size_t kSampleBufferBytes = size_t(4) << 30;
+// Keyed pipeline: records + strata terms of one batch of passes (pt_split.cu), ~530 B per sample
+// at 4x4 strata.  Batches of ~2 M samples keep the persistent sub-path kernel's tail below 1 %.
+constexpr size_t kSplitBufferBytes = size_t(1) << 30;
 
 // ---- host restatement of the per-triangle values the reference derives in addTriangle ----
 struct H3 {
@@ -145,7 +148,11 @@ struct PtContext {
   DeviceBuffer<PtPixelDevice> accumulator;
   DeviceBuffer<double> samples;
   DeviceBuffer<uint32_t> mtHistory;          // fp way: scratch of the per-lane engines (pt_mt19937.cuh)
-  DeviceBuffer<unsigned long long> counters; // [0] ticket, [1] casts
+  DeviceBuffer<double2> records;             // keyed pipeline: camera-ray hits of one batch (pt_split.cu)
+  DeviceBuffer<double> terms;                //   ... one term per (sample, stratum)
+  DeviceBuffer<uint8_t> sampleKind;          //   ... strata terms / colour
+  uint32_t numMaterials{0};
+  DeviceBuffer<unsigned long long> counters; // [0] ticket, [1] casts, [2] records of the batch
   int accWidth{0}, accHeight{0};
 };
 
@@ -288,7 +295,7 @@ int ptb200_context_create(int32_t device, PtContext **out) {
     delete ctx;
     return fail(PTB200_ECUDA, "cudaStreamCreate failed");
   }
-  if (ctx->counters.ensure(2) != cudaSuccess) {
+  if (ctx->counters.ensure(3) != cudaSuccess) {
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return fail(PTB200_ENOMEM, "device allocation failed");
@@ -400,6 +407,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   d.environment[1] = scene->environment[1];
   d.environment[2] = scene->environment[2];
   ctx->scene = d;
+  ctx->numMaterials = scene->numMaterials;
   ctx->haveScene = true;
   return PTB200_OK;
 }
@@ -435,22 +443,36 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
     return PTB200_OK;
   const bool ooWay = opt.rngMode == PTB200_RNG_MT19937_SEQUENTIAL_OO;
   const bool sequential = opt.rngMode == PTB200_RNG_MT19937_SEQUENTIAL || ooWay;
+  const bool fpWay = opt.rngMode == PTB200_RNG_MT19937_PER_PIXEL;
+  int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable, fpWay ? 1 : 0);
+  if (fpWay) { // the megakernel's instantiations for the per-lane engines
+    const int sweep = keyedConfig % 10, shape = (keyedConfig % 100) / 10;
+    keyedConfig = sweep == 6 ? (shape == 2 ? 26 : 6) : 1;
+  }
+  const bool split = !sequential && !fpWay && keyedConfig >= 100;
+  const uint64_t numSub = static_cast<uint64_t>(params->firstBounceUSamples) * static_cast<uint64_t>(params->firstBounceVSamples);
   const size_t pixelsPerPass = sequential ? static_cast<size_t>(params->width) * params->height : ownPixels;
-  size_t passesPerBatch = std::max<size_t>(1, kSampleBufferBytes / (pixelsPerPass * 24));
+  size_t passesPerBatch;
+  if (split) {
+    if (numSub * ownPixels >= (uint64_t(1) << 32))
+      return fail(PTB200_EINVAL, "%llu strata x %u pixels exceed the sub-path index range",
+                  static_cast<unsigned long long>(numSub), ownPixels);
+    const size_t perSample = splitBytesPerSample(static_cast<uint32_t>(numSub));
+    passesPerBatch = std::max<size_t>(1, kSplitBufferBytes / (pixelsPerPass * perSample));
+    passesPerBatch = std::min<size_t>(passesPerBatch, ((uint64_t(1) << 32) - 1) / (numSub * ownPixels));
+  } else {
+    passesPerBatch = std::max<size_t>(1, kSampleBufferBytes / (pixelsPerPass * 24));
+  }
   if (opt.passesPerBatch > 0)
     passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(opt.passesPerBatch));
   passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses));
-  PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
-  const bool fpWay = opt.rngMode == PTB200_RNG_MT19937_PER_PIXEL;
-  int keyedConfig = chooseKeyedConfig(ctx->scene.numTriangles, ctx->filterUsable, fpWay ? 1 : 0);
-  if (fpWay) { // instantiated for the default configurations and the FP64 fallback only
-    const int sweep = keyedConfig % 10, shape = keyedConfig / 10;
-    if (sweep == 6)
-      keyedConfig = shape == 2 ? 26 : 6;
-    else if (sweep == 5)
-      keyedConfig = shape == 2 ? 25 : shape == 4 ? 45 : 5;
-    else
-      keyedConfig = sweep <= 1 ? 1 : sweep == 4 ? (shape == 2 ? 24 : 4) : 3;
+  if (split) {
+    const size_t samples = passesPerBatch * pixelsPerPass;
+    PT_CUDA(ctx->records.ensure(samples * 9));
+    PT_CUDA(ctx->terms.ensure(samples * numSub * 3));
+    PT_CUDA(ctx->sampleKind.ensure(samples));
+  } else {
+    PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
   }
   size_t mtThreads = 0;
   uint32_t mtLimit = 0;
@@ -499,6 +521,46 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.samples = ctx->samples.ptr;
       a.castCounter = ctx->counters.ptr + 1;
       PT_CUDA(launchRenderSequential(a, ctx->stream));
+    } else if (split) {
+      PT_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(unsigned long long), ctx->stream));     // ticket
+      PT_CUDA(cudaMemsetAsync(ctx->counters.ptr + 2, 0, sizeof(unsigned long long), ctx->stream)); // records
+      SplitArgs a{};
+      a.scene = ctx->scene;
+      a.camera = toDeviceCamera(*camera);
+      a.width = static_cast<uint32_t>(params->width);
+      a.height = static_cast<uint32_t>(params->height);
+      a.rowBegin = rowBegin;
+      a.rowStep = rowStep;
+      a.ownPixels = ownPixels;
+      a.totalSamples = ownPixels * static_cast<uint32_t>(batch);
+      a.numPasses = static_cast<uint32_t>(batch);
+      a.numSub = static_cast<uint32_t>(numSub);
+      a.numMaterials = ctx->numMaterials;
+      a.seed = params->seed;
+      a.passBegin = passBegin + done;
+      a.maxDepth = params->maxDepth;
+      a.firstBounceU = params->firstBounceUSamples;
+      a.firstBounceV = params->firstBounceVSamples;
+      a.preview = params->preview;
+      a.firstBounceUPow2 = (a.firstBounceU & (a.firstBounceU - 1)) == 0;
+      a.firstBounceVPow2 = (a.firstBounceV & (a.firstBounceV - 1)) == 0;
+      a.invFirstBounceU = 1.0 / static_cast<double>(a.firstBounceU);
+      a.invFirstBounceV = 1.0 / static_cast<double>(a.firstBounceV);
+      a.records = ctx->records.ptr;
+      a.terms = ctx->terms.ptr;
+      a.sampleKind = ctx->sampleKind.ptr;
+      a.counters = ctx->counters.ptr;
+      a.accumulator = ctx->accumulator.ptr;
+      PT_CUDA(launchRenderSplit(a, ctx->numSms, keyedConfig, ctx->stream));
+      if (events) { // the three kernels of the pipeline are the path-tracing time
+        PT_CUDA(cudaEventRecord(e1, ctx->stream));
+        events->push_back(e0);
+        events->push_back(e1);
+      }
+      if (launches)
+        *launches += 3;
+      done += batch;
+      continue;
     } else {
       PT_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(unsigned long long), ctx->stream));
       KeyedArgs a{};

@@ -249,7 +249,8 @@ def test_every_megakernel_configuration_renders_identically(scene_name, w, h, sc
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
                 root, os.path.join(root, "tests/golden/scenes/%s.ptscene" % scene_name), w, h, w, h)
     outs = []
-    for config in ("1", "0", "2", "3", "4", "13", "24", "43", "5", "6", "25", "26", "35", "46", "56"):
+    for config in ("1", "0", "2", "3", "4", "13", "24", "43", "5", "6", "25", "26", "35", "46", "56",
+                   "101", "106", "121", "126", "136", "146", "166"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
