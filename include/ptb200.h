@@ -158,9 +158,10 @@ int ptb200_device_count(int32_t *count);
 /* ---- one-shot, host buffers in, host buffers out (the reference-facing call) ------------ */
 
 /* Replaces dod::Scene::render.  `out` holds width*height PtPixel, row-major, index
- * x + y*width (ArrayOutput.h:14-17); rows outside the rowBegin/rowStep selection are left
- * zero.  Uses options->device only.  Returns exactly samplesPerPixel samples for every
- * selected pixel (the reference drops its last in-flight passes, Scene.cpp:251; we do not). */
+ * x + y*width (ArrayOutput.h:14-17); rows outside the rowBegin/rowStep selection are not
+ * written (zero-initialise the buffer to read them as "no samples").  Uses options->device
+ * only.  Returns exactly samplesPerPixel samples for every selected pixel (the reference drops
+ * its last in-flight passes, Scene.cpp:251; we do not). */
 int ptb200_render(const PtScene *scene, const PtCamera *camera, const PtRenderParams *params,
                   const PtRenderOptions *options, PtPixel *out, PtProgressFn progress,
                   void *user, PtStats *stats);

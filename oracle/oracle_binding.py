@@ -174,6 +174,14 @@ def ref_render(scene, width, height, spp, max_cpus, seed, out="-", first_u=4, fi
                                first_v, max_depth, out))
 
 
+def ref_passes(scene, width, height, spp, threads, seed, out="-", first_u=4, first_v=4,
+               max_depth=5) -> dict:
+    """The reference's own radiance()/randomRay() for every pass, passes spread fairly over
+    `threads` workers and ALL of them kept (ref_tool `passes`); returns its JSON line."""
+    return json.loads(ref_tool("passes", scene, width, height, spp, threads, seed, first_u,
+                               first_v, max_depth, out))
+
+
 def ref_intersect(scene, rays, tmpdir, which=0, nearer_than="inf") -> np.ndarray:
     """(N,18): hit, distance, inside, pos3, normal3, material 9 doubles."""
     rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)

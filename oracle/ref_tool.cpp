@@ -25,6 +25,7 @@
 #include "util/ObjLoader.h"
 #include "util/RenderParams.h"
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -201,6 +202,7 @@ int usage() {
                "ref_tool check-recipes\n"
                "ref_tool pass NAME W H SEED PASS NU NV MAXDEPTH PREVIEW OUT.f64\n"
                "ref_tool render NAME W H SPP MAXCPUS SEED NU NV MAXDEPTH OUT.raw|-\n"
+               "ref_tool passes NAME W H SPP THREADS SEED NU NV MAXDEPTH OUT.raw|-   (every pass kept)\n"
                "ref_tool intersect NAME|FILE.ptscene WHICH NEARER RAYS.f64 OUT.f64\n"
                "ref_tool fp-pass NAME W H SEED NU NV MAXDEPTH PREVIEW OUT.f64   (fp::render, one pass)\n"
                "ref_tool fp-render NAME W H SPP MAXCPUS SEED NU NV MAXDEPTH OUT.raw|-\n"
@@ -328,6 +330,50 @@ int main(int argc, char **argv) {
       ArrayOutput output = scene.render(cam, p, [](ArrayOutput &) {}); // the unmodified entry point
       const auto t1 = std::chrono::steady_clock::now();
       std::cout.rdbuf(saved);
+      const std::string outPath = argv[11];
+      if (outPath != "-")
+        output.save(absolutePath(outPath));
+      std::printf("{\"seconds\": %.6f, \"total_samples\": %zu, \"pixels\": %d}\n",
+                  std::chrono::duration<double>(t1 - t0).count(), output.totalSamples(),
+                  p.width * p.height);
+      return 0;
+    }
+    if (cmd == "passes" && argc == 12) {
+      // The reference's own per-pass work (the lambda of dod::Scene::render, Scene.cpp:210-217:
+      // its radiance() and Camera::randomRay(), compiled from its sources) with the passes handed
+      // to THREADS workers one at a time and EVERY pass kept — Scene::render itself abandons the
+      // passes still in flight when the last one is launched (Scene.cpp:251).  This is the
+      // reference's arithmetic at the rate a fair scheduler gives it: bench.py's CPU baseline.
+      RenderParams p = sized(std::atoi(argv[3]), std::atoi(argv[4]));
+      p.samplesPerPixel = std::atoi(argv[5]);
+      const int threads = std::max(1, std::atoi(argv[6]));
+      p.seed = std::atoi(argv[7]);
+      p.firstBounceUSamples = std::atoi(argv[8]);
+      p.firstBounceVSamples = std::atoi(argv[9]);
+      p.maxDepth = std::atoi(argv[10]);
+      dod::Scene scene;
+      const Camera cam = makeScene(argv[2], scene, p.width, p.height);
+      std::atomic<int> nextPass{0};
+      std::vector<ArrayOutput> partial(threads, ArrayOutput(p.width, p.height));
+      const auto t0 = std::chrono::steady_clock::now();
+      std::vector<std::thread> workers;
+      for (int t = 0; t < threads; ++t)
+        workers.emplace_back([&, t] {
+          for (int pass = nextPass++; pass < p.samplesPerPixel; pass = nextPass++) {
+            std::mt19937 rng(p.seed + pass);
+            for (int y = 0; y < p.height; ++y)
+              for (int x = 0; x < p.width; ++x) {
+                auto ray = cam.randomRay(x, y, rng);
+                partial[t].addSamples(x, y, scene.radiance(rng, ray, 0, p), 1);
+              }
+          }
+        });
+      for (auto &w : workers)
+        w.join();
+      ArrayOutput output(p.width, p.height);
+      for (auto &part : partial)
+        output += part;
+      const auto t1 = std::chrono::steady_clock::now();
       const std::string outPath = argv[11];
       if (outPath != "-")
         output.save(absolutePath(outPath));

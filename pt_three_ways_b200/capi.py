@@ -197,6 +197,7 @@ def render(scene, camera18, params: PtRenderParams, options: PtRenderOptions | N
 
 SWEEP_ONE_STAGE, SWEEP_TWO_STAGE_FP64, SWEEP_FP32_STAGE0, SWEEP_FP32X2_STAGE0, SWEEP_FP32X2_STAGE0_T = 0, 1, 2, 3, 4
 SWEEP_FP32X2_SIGNS_T, SWEEP_FP32X2_SIGNS = 5, 6  # 4 and 3 with the stage-0 decisions kept in sign bits
+SWEEP_FP32X2_MOMENT = 7  # 6 in moment (Pluecker) form: dot products against per-triangle constants
 
 
 def intersect(scene, rays, which=0, nearer_than=float("inf"), device=0, warp_cooperative=False,
@@ -204,19 +205,21 @@ def intersect(scene, rays, which=0, nearer_than=float("inf"), device=0, warp_coo
     m = scene if isinstance(scene, MarshalledScene) else MarshalledScene(scene)
     rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
     out = np.zeros(rays.shape[0], dtype=HIT_DTYPE)
-    flags = (0x100 if warp_cooperative else 0) | (((sweep + 1) << 9) if sweep is not None else 0)
+    flags = 0x100 if warp_cooperative else 0
+    if sweep is not None:
+        flags |= (((sweep + 1) & 7) << 9) | (((sweep + 1) & 8) << 11)
     _check(lib().ptb200_intersect(C.byref(m.abi), device, which | flags,
                                   nearer_than, rays.shape[0], rays.ctypes.data, out.ctypes.data))
     return out
 
 
-def audit_stage0(scene, rays, device=0) -> dict:
+def audit_stage0(scene, rays, device=0, moment_form=False) -> dict:
     """Test hook: runs the FP32 stage-0 filter and the exact test on every (ray, triangle) pair
     and counts pairs / stage-0 survivors / exact accepts / violations (accepted but filtered)."""
     m = scene if isinstance(scene, MarshalledScene) else MarshalledScene(scene)
     rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
     out = np.zeros(max(1, rays.shape[0]), dtype=HIT_DTYPE)
-    _check(lib().ptb200_intersect(C.byref(m.abi), device, 0x1000, float("inf"), rays.shape[0],
+    _check(lib().ptb200_intersect(C.byref(m.abi), device, 0x1000 | (0x2000 if moment_form else 0), float("inf"), rays.shape[0],
                                   rays.ctypes.data, out.ctypes.data))
     counters = out.view(np.uint64)[:4]
     return dict(pairs=int(counters[0]), survivors=int(counters[1]), accepts=int(counters[2]),

@@ -31,6 +31,7 @@ struct DeviceScene {
   const uint32_t *sphereMaterial;
   const double *materials;    // [numMaterials][10] MaterialSpec order + 1/indexOfRefraction
   const float *triFilter;     // [numTiles][tileTris/4][14][4] fp32 stage-0 data (buildFilterKernel)
+  const float *triMoment;     // [numTiles][tileTris/4][19][4] fp32 stage-0 data in moment (Pluecker) form
   const double *triExact;     // [numTiles*tileTris][10] AoS copy of the 9 sweep doubles (+pad) for the
                               //   survivors' exact test: one address, five 16-byte loads
   uint32_t numTriangles;
@@ -438,6 +439,138 @@ __device__ __forceinline__ void sweepTileStage0Signs(const float *__restrict__ f
       stage0Reject2<kRejectNegativeT>(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6),
                                       PT_HI(7), PT_HI(8), PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), PT_HI(13),
                                       r2, r2bits, r3);
+#undef PT_LO
+#undef PT_HI
+      rejectedHi = __funnelshift_l(rejectedLo, rejectedHi, 4);
+      rejectedLo = __funnelshift_l(r0, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r1, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r2bits, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r3, rejectedLo, 1);
+    }
+    // left-align: triangle chunk + k at bit 63 - k; the slots past chunkEnd read "rejected"
+    unsigned long long keep = ~((static_cast<unsigned long long>(rejectedHi) << 32) | rejectedLo)
+                              << (64 - (chunkEnd - chunk));
+    while (keep) {
+      const int k = __clzll(static_cast<long long>(keep));
+      keep &= ~(0x8000000000000000ull >> k);
+      const int i = chunk + k;
+      const double2 *record = reinterpret_cast<const double2 *>(exact + 10 * static_cast<size_t>(i));
+      const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
+                    a4 = __ldg(record + 4);
+      testTriangle<kFpWay>(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d, firstIndex + i, best);
+    }
+  }
+}
+
+// ---- stage 0 in moment (Pluecker) form: sweep variant 7 -----------------------------------------
+// Moller-Trumbore's three numerators are scalar triple products, so with the ray's moment
+// m = o x d (per ray, once, in FP64) and per-triangle constants they are plain dot products:
+//     det = e1 . (d x e2)            = d . (e2 x e1)
+//     X   = (o - v0) . (d x e2)      = e2 . m + d . (v0 x e2)
+//     Y   = d . ((o - v0) x e1)      = (-e1) . m + d . (-(v0 x e1))
+// i.e. 15 packed operations per pair of triangles instead of 24 (no per-triangle cross products),
+// on five FP32 vectors per triangle (built in FP64 by buildFilterKernel, rounded once).  Forward
+// error analysis with u = 2^-24, |d| = 1, inputs rounded to FP32 (1 roundoff each):
+//     |det32 - det| <= (gamma_3 + 2u) |e1||e2|        ~  5.1 u |e1||e2|
+//     |X32 - X|     <= (gamma_6 + 2u) |e2| (|o|+|v0|) ~  8.2 u r|e2|      (|m| <= |o|, |v0 x e2| <= |v0||e2|)
+//     |Y32 - Y|     <= likewise                       ~  8.2 u r|e1|
+// all well inside the bounds Ed, Ex, Ey = 64 u x the same magnitudes that buildFilterKernel stores
+// for the classic form (which needs 13..18 u), so the decision logic and its soundness argument
+// are stage0Reject2()'s unchanged: reject only if |det32| > Ed and one of s*X32 < -2Ex,
+// s*Y32 < -2Ey, s*(X32+Y32) > |det32|(1+2^-20) + Ed + Ex + Ey, all taken as sign bits.
+constexpr int kMomentFloats = 19; // nn xyz, e2 xyz, a2 xyz, -e1 xyz, -a1 xyz, Ed, 2Ex, 2Ey, K3
+struct MomentRay {
+  float dx, dy, dz, mx, my, mz;
+  uint32_t one; // 0x3f800000 held in a register (a LOP3 takes a single immediate)
+};
+__device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
+__device__ __forceinline__ void stage0RejectMoment(float2 nx, float2 ny, float2 nz, float2 e2x, float2 e2y,
+                                                   float2 e2z, float2 a2x, float2 a2y, float2 a2z, float2 f1x,
+                                                   float2 f1y, float2 f1z, float2 b1x, float2 b1y, float2 b1z,
+                                                   float2 ed, float2 kx, float2 ky, float2 k3, const MomentRay &r,
+                                                   uint32_t &rejectA, uint32_t &rejectB) {
+  const float2 det = __ffma2_rn(splat(r.dz), nz, __ffma2_rn(splat(r.dy), ny, __fmul2_rn(splat(r.dx), nx)));
+  float2 x = __ffma2_rn(splat(r.my), e2y, __fmul2_rn(splat(r.mx), e2x));
+  x = __ffma2_rn(splat(r.mz), e2z, x);
+  x = __ffma2_rn(splat(r.dx), a2x, x);
+  x = __ffma2_rn(splat(r.dy), a2y, x);
+  x = __ffma2_rn(splat(r.dz), a2z, x);
+  float2 y = __ffma2_rn(splat(r.my), f1y, __fmul2_rn(splat(r.mx), f1x));
+  y = __ffma2_rn(splat(r.mz), f1z, y);
+  y = __ffma2_rn(splat(r.dx), b1x, y);
+  y = __ffma2_rn(splat(r.dy), b1y, y);
+  y = __ffma2_rn(splat(r.dz), b1z, y);
+  uint32_t sA, sB; // copysign(1, det)
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(sA) : "r"(__float_as_uint(det.x)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(sB) : "r"(__float_as_uint(det.y)), "r"(r.one));
+  const float2 s = make_float2(__uint_as_float(sA), __uint_as_float(sB));
+  const float2 adet = make_float2(fabsf(det.x), fabsf(det.y));
+  const float2 a = __ffma2_rn(x, s, kx);
+  const float2 b = __ffma2_rn(y, s, ky);
+  const float2 bound = __ffma2_rn(adet, make_float2(1.0f + 0x1p-20f, 1.0f + 0x1p-20f), k3);
+  const float2 e = __ffma2_rn(neg2(__fadd2_rn(x, y)), s, bound);
+  const float2 f = __fadd2_rn(ed, neg2(adet));
+  rejectA = (__float_as_uint(a.x) | __float_as_uint(b.x) | __float_as_uint(e.x)) & __float_as_uint(f.x);
+  rejectB = (__float_as_uint(a.y) | __float_as_uint(b.y) | __float_as_uint(e.y)) & __float_as_uint(f.y);
+}
+// The same decision for ONE triangle in scalar FP32 (same operations, same rounding): the audit
+// kernel's view of the filter.
+__device__ __forceinline__ bool stage0KeepMoment(const float *f, int stride, const MomentRay &r) {
+  const float det = fmaf(r.dz, f[2 * stride], fmaf(r.dy, f[1 * stride], r.dx * f[0]));
+  float x = fmaf(r.my, f[4 * stride], r.mx * f[3 * stride]);
+  x = fmaf(r.mz, f[5 * stride], x);
+  x = fmaf(r.dx, f[6 * stride], x);
+  x = fmaf(r.dy, f[7 * stride], x);
+  x = fmaf(r.dz, f[8 * stride], x);
+  float y = fmaf(r.my, f[10 * stride], r.mx * f[9 * stride]);
+  y = fmaf(r.mz, f[11 * stride], y);
+  y = fmaf(r.dx, f[12 * stride], y);
+  y = fmaf(r.dy, f[13 * stride], y);
+  y = fmaf(r.dz, f[14 * stride], y);
+  const float s = copysignf(1.0f, det), adet = fabsf(det);
+  const float a = fmaf(x, s, f[16 * stride]);
+  const float b = fmaf(y, s, f[17 * stride]);
+  const float bound = fmaf(adet, 1.0f + 0x1p-20f, f[18 * stride]);
+  const float e = fmaf(-(x + y), s, bound);
+  const float g = f[15 * stride] - adet;
+  const uint32_t reject = (__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(e)) & __float_as_uint(g);
+  return (reject & 0x80000000u) == 0;
+}
+__device__ __forceinline__ MomentRay makeMomentRay(V3 o, V3 d) {
+  const V3 m = cross(o, d);
+  uint32_t one;
+  asm("mov.u32 %0, 0x3f800000;" : "=r"(one)); // opaque to constant folding
+  return MomentRay{static_cast<float>(d.x), static_cast<float>(d.y), static_cast<float>(d.z),
+                   static_cast<float>(m.x), static_cast<float>(m.y), static_cast<float>(m.z), one};
+}
+
+// Sweeps a staged tile of moment-form data; same survivor bookkeeping as sweepTileStage0Signs().
+template <bool kFpWay = false>
+__device__ __forceinline__ void sweepTileStage0Moment(const float *__restrict__ filter,
+                                                      const double *__restrict__ exact, int count,
+                                                      int firstIndex, V3 o, V3 d, Nearest &best) {
+  const MomentRay r = makeMomentRay(o, d);
+#pragma unroll 1
+  for (int chunk = 0; chunk < count; chunk += 64) {
+    const int chunkEnd = min(count, chunk + 64);
+    uint32_t rejectedHi = 0xffffffffu, rejectedLo = 0xffffffffu;
+    const float4 *group = reinterpret_cast<const float4 *>(filter) + (chunk >> 2) * kMomentFloats;
+    const float4 *const groupEnd = reinterpret_cast<const float4 *>(filter) + (chunkEnd >> 2) * kMomentFloats;
+#pragma unroll 1
+    for (; group != groupEnd; group += kMomentFloats) {
+      float4 a[kMomentFloats];
+#pragma unroll
+      for (int k = 0; k < kMomentFloats; ++k)
+        a[k] = group[k];
+      uint32_t r0, r1, r2bits, r3;
+#define PT_LO(k) make_float2(a[k].x, a[k].y)
+#define PT_HI(k) make_float2(a[k].z, a[k].w)
+      stage0RejectMoment(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6), PT_LO(7), PT_LO(8),
+                         PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), PT_LO(13), PT_LO(14), PT_LO(15), PT_LO(16),
+                         PT_LO(17), PT_LO(18), r, r0, r1);
+      stage0RejectMoment(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6), PT_HI(7), PT_HI(8),
+                         PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), PT_HI(13), PT_HI(14), PT_HI(15), PT_HI(16),
+                         PT_HI(17), PT_HI(18), r, r2bits, r3);
 #undef PT_LO
 #undef PT_HI
       rejectedHi = __funnelshift_l(rejectedLo, rejectedHi, 4);

@@ -784,7 +784,9 @@ __global__ void intersectKernel(const __grid_constant__ IntersectArgs args) {
     if (args.which != 1) {
       for (uint32_t j = 0; j < scene.numTiles; ++j) {
         const unsigned char *tile = stream.acquire();
-        if (args.sweep == 6)
+        if (args.sweep == 7)
+          sweepStagedTile<7>(scene, tile, j, o, d, best);
+        else if (args.sweep == 6)
           sweepStagedTile<6>(scene, tile, j, o, d, best);
         else if (args.sweep == 5)
           sweepStagedTile<5>(scene, tile, j, o, d, best);
@@ -875,6 +877,20 @@ __global__ void buildFilterKernel(const __grid_constant__ BuildFilterArgs args) 
   dst[11 * 4] = fky;
   dst[12 * 4] = fk3;
   dst[13 * 4] = fkt;
+  // Moment (Pluecker) form for sweep variant 7, blocked [tile][group of 4][19][4]: the per-triangle
+  // constants of stage0RejectMoment(), evaluated in FP64 and rounded once; the same bounds.
+  float *mom = args.outMoment + (static_cast<size_t>(tile) * (scene.tileTris / 4) + within / 4) * (kMomentFloats * 4) +
+               within % 4;
+  const V3 v0 = mk(v[0], v[1], v[2]), e1 = mk(v[3], v[4], v[5]), e2 = mk(v[6], v[7], v[8]);
+  const V3 nn = cross(e2, e1), a2 = cross(v0, e2), a1 = cross(v0, e1);
+  const double moment[15] = {nn.x, nn.y, nn.z, e2.x, e2.y, e2.z, a2.x, a2.y, a2.z,
+                             -e1.x, -e1.y, -e1.z, -a1.x, -a1.y, -a1.z};
+  for (int k = 0; k < 15; ++k)
+    mom[k * 4] = __double2float_rn(moment[k]);
+  mom[15 * 4] = fed;
+  mom[16 * 4] = fkx;
+  mom[17 * 4] = fky;
+  mom[18 * 4] = fk3;
 }
 
 // For every (ray, triangle): does stage 0 keep it, does the exact test accept it (with no
@@ -888,14 +904,19 @@ __global__ void auditStage0Kernel(const __grid_constant__ AuditArgs args) {
     const V3 d = mk(args.rays[6 * ray + 3], args.rays[6 * ray + 4], args.rays[6 * ray + 5]);
     const Stage0Ray r{static_cast<float>(o.x), static_cast<float>(o.y), static_cast<float>(o.z),
                       static_cast<float>(d.x), static_cast<float>(d.y), static_cast<float>(d.z)};
+    const MomentRay momentRay = makeMomentRay(o, d);
     for (uint32_t index = 0; index < scene.numTriangles; ++index) {
       const uint32_t tile = index / scene.tileTris, i = index % scene.tileTris;
       const float *f = scene.triFilter +
                        (static_cast<size_t>(tile) * (scene.tileTris / 4) + i / 4) * (kFilterFloats * 4) + i % 4;
       const double *e = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris + i;
       const uint32_t n = scene.tileTris;
-      const bool keep = stage0Keep(f[0], f[4], f[8], f[12], f[16], f[20], f[24], f[28], f[32], f[36], f[40], f[44],
-                                   f[48], f[52], r);
+      const float *g = scene.triMoment +
+                       (static_cast<size_t>(tile) * (scene.tileTris / 4) + i / 4) * (kMomentFloats * 4) + i % 4;
+      const bool keep = args.momentForm
+                            ? stage0KeepMoment(g, 4, momentRay)
+                            : stage0Keep(f[0], f[4], f[8], f[12], f[16], f[20], f[24], f[28], f[32], f[36], f[40], f[44],
+                                         f[48], f[52], r);
       Nearest best{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim};
       testTriangle(mk(e[0], e[n], e[2 * n]), mk(e[3 * n], e[4 * n], e[5 * n]), mk(e[6 * n], e[7 * n], e[8 * n]),
                    o, d, static_cast<int>(index), best);
@@ -986,9 +1007,9 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable, int way) {
   if (forced >= 0)
     return forced;
   const bool small = numTriangles <= 512;
-  const int sweep = filterUsable ? 6 : 1;
   if (way == 1)
-    return sweep; // the fp way: the megakernel, two CTAs per SM
+    return filterUsable ? 6 : 1; // the fp way: the megakernel, two CTAs per SM
+  const int sweep = filterUsable ? 7 : 1;
   // the dod estimator with keyed draws: the three-kernel pipeline of pt_split.cu (100 + ...)
   return 100 + 10 * (small ? 2 : 0) + sweep;
 }

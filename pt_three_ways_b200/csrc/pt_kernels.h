@@ -48,9 +48,11 @@ struct SplitArgs {
   uint32_t width, height;
   int32_t rowBegin, rowStep;
   uint32_t ownPixels;              // pixels of the selected rows
-  uint32_t totalSamples;           // ownPixels * passes of this batch; totalSamples * numSub < 2^32
+  uint32_t totalSamples;           // ownPixels * passes of this batch; totalSamples * numSub < 2^31
   uint32_t numPasses;              // passes of this batch
   uint32_t numSub;                 // firstBounceU * firstBounceV
+  int32_t numSubShift;             // log2(numSub) when it is a power of two, else -1
+  int32_t firstBounceVShift;       // likewise for firstBounceV
   uint32_t numMaterials;
   int32_t seed, passBegin;         // pass s of the batch uses key seed + passBegin + s
   int32_t maxDepth, firstBounceU, firstBounceV, preview;
@@ -89,7 +91,8 @@ struct ReduceArgs {
 
 struct BuildFilterArgs {
   DeviceScene scene;
-  float *out;                      // [numTiles][13][tileTris]
+  float *out;                      // [numTiles][tileTris/4][14][4]
+  float *outMoment;                // [numTiles][tileTris/4][19][4] (sweep variant 7)
   double originBound;              // >= |o| for every ray origin of the coming launch
 };
 
@@ -97,6 +100,7 @@ struct AuditArgs {                 // test hook: stage 0 must never reject what 
   DeviceScene scene;
   const double *rays;
   uint32_t numRays;
+  int32_t momentForm;              // audit the moment-form filter of sweep variant 7 instead
   unsigned long long *counters;    // [0] (ray,triangle) pairs, [1] stage-0 survivors,
                                    // [2] exact accepts, [3] VIOLATIONS: exact accept but stage-0 reject
 };

@@ -75,7 +75,9 @@ __device__ __forceinline__ double kernelCos(double r) {
   p = fma(p, z, 4.16666666666666019037e-02);
   return fma(z * z, p, fma(-0.5, z, 1.0));
 }
-static __device__ __noinline__ void sinCos(double x, double &s, double &c) {
+// Out of line (one copy for every caller), results returned BY VALUE: reference parameters of a
+// non-inlined function travel through local memory.
+static __device__ __noinline__ double2 sinCosPair(double x) { // {sin x, cos x}
   const double kd = rint(x * 6.36619772367581382433e-01); // round half to even
   const int k = static_cast<int>(kd);
   double r = fma(-kd, 1.57079632673412561417e+00, x);
@@ -84,8 +86,12 @@ static __device__ __noinline__ void sinCos(double x, double &s, double &c) {
   const double cr = kernelCos(r);
   const double a = (k & 1) ? cr : sr;
   const double b = (k & 1) ? sr : cr;
-  s = (k & 2) ? -a : a;
-  c = ((k + 1) & 2) ? -b : b;
+  return make_double2((k & 2) ? -a : a, ((k + 1) & 2) ? -b : b);
+}
+__device__ __forceinline__ void sinCos(double x, double &s, double &c) {
+  const double2 pair = sinCosPair(x);
+  s = pair.x;
+  c = pair.y;
 }
 __device__ __forceinline__ double asinCore(double z) {
   double p = fma(3.47933107596021167570e-05, z, 7.91534994289814532176e-04);

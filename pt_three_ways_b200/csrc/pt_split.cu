@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(kBlock) primaryHitsKernel(const __grid_constan
 // =============================================================================================
 // 2. Sub-paths.
 // =============================================================================================
-constexpr unsigned long long kTicketGrab = 64; // tickets a warp takes per atomic (>= 32)
+constexpr uint32_t kTicketGrab = 64; // tickets a warp takes per atomic (>= 32)
 
 // Levels 1.. of a sub-path: material index and branch taken, for the unwind.  Paths of the
 // reference's default depth keep them in one 64-bit register (16 bits per level); deeper ones in
@@ -220,6 +220,34 @@ struct LevelStack<true> {
   }
 };
 
+// Surface word flag: the local basis of this surface has not been computed (a sphere hit inside
+// the sub-path kernel).  OrthoNormalBasis::fromZ(hit.normal) is evaluated before the sampling loop
+// in the reference (Scene.cpp:152) but only hemisphereSample reads it (:170), so evaluating it
+// on the diffuse branch only is the same arithmetic on the same values.
+constexpr uint32_t kLazyBasisFlag = 0x80000000u;
+
+// The specular-only part of coneSample() (Samples.cpp:6-19): everything up to the final
+// normalised(basis.transform(cos(t)*r, sin(t)*r, z)), which the diffuse lanes share.  Returns true
+// when the cone is degenerate and the mirror direction itself is the answer.
+__device__ __forceinline__ bool coneSetup(V3 mirror, double coneTheta, double u, double v, V3 &bx, V3 &by, V3 &bz,
+                                          double &angle, double &radius, double &zScale) {
+  if (coneTheta < kEpsilon)
+    return true;
+  coneTheta = coneTheta * (1.0 - ieeeDiv(2.0 * arcCos(u), kPi));
+  sinCos(coneTheta, radius, zScale);
+  angle = v * 2 * kPi;
+  const Basis basis = basisFromZ(mirror);
+  bx = basis.x;
+  by = basis.y;
+  bz = mirror;
+  return false;
+}
+
+// Per-thread state is kept small on purpose: the ray, six words of path bookkeeping and the level
+// stack.  The Surface a bounce leaves from never lives in registers across phases: a hit writes it
+// to the thread's shared-memory slot (same 9 x 16-byte layout as a camera-hit record), a new
+// sub-path points at its record in global memory, and the bounce reads whichever through one
+// generic pointer.
 template <int kBlock, int kMinBlocks, int kSweep, bool kDeep>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid_constant__ SplitArgs args) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -233,63 +261,63 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
   const bool resident = scene.numTiles <= 1;
   if (resident && scene.numTiles == 1)
     stream.acquire(); // the one tile stays in buffer 0 for the whole launch
+  double2 *const slot = reinterpret_cast<double2 *>(smemRaw + smemAfterTiles(scene.numSpheres, scene.tileTris,
+                                                                             scene.numTiles, kSweep)) +
+                        kRecordQuads * threadIdx.x;
 
   const unsigned lane = threadIdx.x & 31u;
   const uint32_t numSub = args.numSub;
-  const unsigned long long totalItems = args.counters[2] * numSub; // records the first kernel appended
-  const V3 environment = mk(scene.environment[0], scene.environment[1], scene.environment[2]);
+  const uint32_t totalItems = static_cast<uint32_t>(args.counters[2]) * numSub; // records x strata, < 2^31
+  unsigned int *const ticket = reinterpret_cast<unsigned int *>(args.counters);
 
   // ---- per-lane path state ----
   V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
   int depth = 0;              // depth of the ray in flight (>= 1 after the first bounce)
   uint32_t pixel = 0, key0 = 0, subPath = 0;
   uint32_t termIndex = 0;     // sample * numSub + subPath
-  uint32_t primaryMaterial = 0;
-  bool primarySpecular = false;
+  uint32_t primary = 0;       // the camera hit's material | specular pick << 31
+  uint32_t casts = 0;         // per lane and launch: far below 2^32
   LevelStack<kDeep> stack;
   stack.reset();
-  Surface surface{};          // what the next bounce leaves from
+  const double2 *surface = slot; // what the next bounce leaves from (generic: record or slot)
   bool needItem = true, finished = false;
-  unsigned long long poolNext = 0, poolEnd = 0; // this warp's tickets (warp-uniform)
-  unsigned long long warpCasts = 0;             // warp-uniform
+  uint32_t poolNext = 0, poolEnd = 0; // this warp's tickets (warp-uniform)
 
   for (;;) {
     // ---- 1. the next sub-path for lanes whose path has ended ----
     const unsigned needMask = __ballot_sync(kFullMask, needItem);
     if (needMask) {
-      const unsigned long long want = static_cast<unsigned long long>(__popc(needMask));
-      const unsigned long long rank = static_cast<unsigned long long>(__popc(needMask & ((1u << lane) - 1u)));
-      const unsigned long long available = poolEnd - poolNext;
-      unsigned long long item;
+      const uint32_t want = static_cast<uint32_t>(__popc(needMask));
+      const uint32_t rank = static_cast<uint32_t>(__popc(needMask & ((1u << lane) - 1u)));
+      const uint32_t available = poolEnd - poolNext;
+      uint32_t item;
       if (available >= want) {
         item = poolNext + rank;
         poolNext += want;
       } else { // the rest of the old pool, then a fresh one
-        unsigned long long base = 0;
+        uint32_t base = 0;
         if (lane == 0)
-          base = atomicAdd(args.counters, kTicketGrab);
+          base = atomicAdd(ticket, static_cast<unsigned int>(kTicketGrab));
         base = __shfl_sync(kFullMask, base, 0);
         item = rank < available ? poolNext + rank : base + (rank - available);
         poolNext = base + (want - available);
-        poolEnd = base + kTicketGrab;
+        poolEnd = base + static_cast<uint32_t>(kTicketGrab);
       }
       if (needItem) {
         needItem = false;
         if (item >= totalItems) {
           finished = true;
         } else {
-          const uint32_t recordIndex = static_cast<uint32_t>(item / numSub);
-          subPath = static_cast<uint32_t>(item) - recordIndex * numSub;
-          const double2 *record = args.records + kRecordQuads * static_cast<size_t>(recordIndex);
-          const double2 q0 = record[0], q1 = record[1], q2 = record[2], q3 = record[3], q4 = record[4],
-                        q5 = record[5], q6 = record[6], q7 = record[7], q8 = record[8];
-          surface.position = mk(q0.x, q0.y, q1.x);
-          surface.normal = mk(q1.y, q2.x, q2.y);
-          surface.incoming = mk(q3.x, q3.y, q4.x);
-          surface.basisX = mk(q4.y, q5.x, q5.y);
-          surface.basisY = mk(q6.x, q6.y, q7.x);
-          surface.reflectivity = q7.y;
-          surface.material = lowWord(q8.x);
+          uint32_t recordIndex;
+          if (args.numSubShift >= 0) {
+            recordIndex = item >> args.numSubShift;
+            subPath = item & (numSub - 1u);
+          } else {
+            recordIndex = item / numSub;
+            subPath = item - recordIndex * numSub;
+          }
+          surface = args.records + kRecordQuads * static_cast<size_t>(recordIndex);
+          const double2 q8 = surface[8];
           pixel = highWord(q8.x);
           key0 = lowWord(q8.y);
           termIndex = highWord(q8.y) * numSub + subPath;
@@ -315,46 +343,68 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
       double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
       if (depth == 0) {
         // u-major strata (Scene.cpp:155-156); x / n == x * (1/n) exactly when n is a power of two
-        const double su = static_cast<double>(subPath / static_cast<uint32_t>(args.firstBounceV)) + ru;
-        const double sv = static_cast<double>(subPath % static_cast<uint32_t>(args.firstBounceV)) + rv;
+        uint32_t stratumU, stratumV;
+        if (args.firstBounceVShift >= 0) {
+          stratumU = subPath >> args.firstBounceVShift;
+          stratumV = subPath & (static_cast<uint32_t>(args.firstBounceV) - 1u);
+        } else {
+          stratumU = subPath / static_cast<uint32_t>(args.firstBounceV);
+          stratumV = subPath - stratumU * static_cast<uint32_t>(args.firstBounceV);
+        }
+        const double su = static_cast<double>(stratumU) + ru;
+        const double sv = static_cast<double>(stratumV) + rv;
         u = args.firstBounceUPow2 ? su * args.invFirstBounceU : ieeeDiv(su, static_cast<double>(args.firstBounceU));
         v = args.firstBounceVPow2 ? sv * args.invFirstBounceV : ieeeDiv(sv, static_cast<double>(args.firstBounceV));
       }
-      // coneSample() / hemisphereSample() (Samples.cpp:6-30) end in the same
-      // normalised(basis.transform(cos(t)*r, sin(t)*r, z)): the few specular lanes only prepare
-      // its inputs, then every lane runs that tail together.
-      const bool specular = rp < surface.reflectivity;
-      Basis frame{surface.basisX, surface.basisY, surface.normal};
+      const double2 q7 = surface[7], q8 = surface[8];
+      const uint32_t surfaceWord = lowWord(q8.x);
+      const uint32_t material = surfaceWord & ~kLazyBasisFlag;
+      const bool specular = rp < q7.y; // p < reflectivity
+      const double2 q1 = surface[1], q2 = surface[2];
+      V3 frameZ = mk(q1.y, q2.x, q2.y); // the surface normal
+      V3 frameX, frameY;
       double angle = (2 * kPi) * u, radius = 0, zScale = 0;
       bool direct = false;
       V3 newDirection = mk(0, 0, 0);
+      // coneSample() / hemisphereSample() (Samples.cpp:6-30) end in the same
+      // normalised(basis.transform(cos(t)*r, sin(t)*r, z)): the few specular lanes only prepare
+      // its inputs, then every lane runs that tail together.
       if (specular) {
-        newDirection = reflect(surface.normal, surface.incoming);
-        direct = coneSampleSetup(newDirection, materialOf(scene, surface.material).coneAngle(), u, v, frame,
-                                 angle, radius, zScale);
+        const double2 q3 = surface[3], q4 = surface[4];
+        newDirection = reflect(frameZ, mk(q3.x, q3.y, q4.x));
+        direct = coneSetup(newDirection, materialOf(scene, material).coneAngle(), u, v, frameX, frameY, frameZ,
+                           angle, radius, zScale);
       } else {
+        if (surfaceWord & kLazyBasisFlag) {
+          const Basis basis = basisFromZ(frameZ);
+          frameX = basis.x;
+          frameY = basis.y;
+        } else {
+          const double2 q4 = surface[4], q5 = surface[5], q6 = surface[6];
+          frameX = mk(q4.y, q5.x, q5.y);
+          frameY = mk(q6.x, q6.y, q7.x);
+        }
         radius = ieeeSqrt(v);
         zScale = ieeeSqrt(1 - v);
       }
       if (!direct) {
         double sinT, cosT;
         sinCos(angle, sinT, cosT);
-        newDirection = normalised(transform(frame, mk(cosT * radius, sinT * radius, zScale)));
+        newDirection = normalised(transform(Basis{frameX, frameY, frameZ}, mk(cosT * radius, sinT * radius, zScale)));
       }
-      if (depth == 0) {
-        primaryMaterial = surface.material;
-        primarySpecular = specular;
-      } else {
-        stack.set(depth, surface.material, specular);
-      }
-      origin = surface.position;
+      if (depth == 0)
+        primary = material | (specular ? 0x80000000u : 0u);
+      else
+        stack.set(depth, material, specular);
+      const double2 q0 = surface[0];
+      origin = mk(q0.x, q0.y, q1.x);
       direction = newDirection;
       ++depth;
+      ++casts;
     }
     __syncwarp();
 
     // ---- 3. cast ----
-    warpCasts += static_cast<unsigned long long>(__popc(__ballot_sync(kFullMask, tracing)));
     const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, origin, direction);
 
     // ---- 4. the hit becomes the next bounce's surface, or the path ends ----
@@ -362,14 +412,63 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
     V3 incoming = mk(0, 0, 0);
     if (tracing) {
       if (best.prim == kNoPrim) {
-        incoming = environment; // Scene.cpp:132-133
+        incoming = mk(scene.environment[0], scene.environment[1], scene.environment[2]); // Scene.cpp:132-133
         ended = true;
       } else if (depth + 1 >= args.maxDepth) {
         // Deepest level: its sampling loop runs, but every child returns Vec3() (Scene.cpp:128-129).
         incoming = shadeTerm(materialOf(scene, hitMaterial(scene, best)), true, mk(0, 0, 0));
         ended = true;
-      } else {
-        surface = surfaceOfHit(scene, stream.spheres(), origin, direction, best);
+      } else { // Scene.cpp:135-152 into the slot
+        const V3 position = positionAlong(origin, direction, best.t);
+        V3 normal;
+        uint32_t word;
+        bool inside;
+        double2 q4 = make_double2(direction.z, 0.0), q5 = make_double2(0.0, 0.0), q6 = q5;
+        double basisYz = 0.0;
+        if (best.prim < 0) { // sphere epilogue (Scene.cpp:38-48); its basis is left to the bounce
+          const int i = -best.prim - 1;
+          const double4 s = stream.spheres()[i];
+          const V3 outward = normalised(sub(position, mk(s.x, s.y, s.z)));
+          inside = dot(outward, direction) > 0;
+          normal = inside ? neg(outward) : outward;
+          word = __ldg(scene.sphereMaterial + i) | kLazyBasisFlag;
+        } else { // triangle epilogue (Scene.cpp:99-112), normal and bases precomputed at upload
+          const double4 *record = scene.triShade + 4 * static_cast<size_t>(best.prim);
+          const double4 r0 = ldgDouble4(record);
+          const double4 r2 = ldgDouble4(record + 2);
+          inside = best.det < kEpsilon; // backfacing
+          word = static_cast<uint32_t>(r0.w);
+          if (inside) {
+            const double4 r3 = ldgDouble4(record + 3);
+            normal = mk(-r0.x, -r0.y, -r0.z);
+            q4.y = r2.z;
+            q5 = make_double2(r2.w, r3.x);
+            q6 = make_double2(r3.y, r3.z);
+            basisYz = r3.w;
+          } else {
+            const double4 r1 = ldgDouble4(record + 1);
+            normal = mk(r0.x, r0.y, r0.z);
+            q4.y = r1.x;
+            q5 = make_double2(r1.y, r1.z);
+            q6 = make_double2(r1.w, r2.x);
+            basisYz = r2.y;
+          }
+        }
+        HitInfo hit;
+        hit.position = position;
+        hit.normal = normal;
+        hit.inside = inside;
+        const double reflectivity = hitReflectivity(materialOf(scene, word & ~kLazyBasisFlag), hit, direction);
+        slot[0] = make_double2(position.x, position.y);
+        slot[1] = make_double2(position.z, normal.x);
+        slot[2] = make_double2(normal.y, normal.z);
+        slot[3] = make_double2(direction.x, direction.y);
+        slot[4] = q4;
+        slot[5] = q5;
+        slot[6] = q6;
+        slot[7] = make_double2(basisYz, reflectivity);
+        slot[8] = make_double2(packWords(word, 0u), 0.0);
+        surface = slot;
       }
     }
     __syncwarp();
@@ -383,11 +482,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
         stack.get(level, material, specular);
         incoming = shadeTerm(materialOf(scene, material), specular, incoming);
       }
-      const V3 term = shadeTerm(materialOf(scene, primaryMaterial), primarySpecular, incoming);
-      double *slot = args.terms + 3 * static_cast<size_t>(termIndex);
-      slot[0] = term.x;
-      slot[1] = term.y;
-      slot[2] = term.z;
+      const V3 term = shadeTerm(materialOf(scene, primary & 0x7fffffffu), (primary >> 31) != 0, incoming);
+      double *out = args.terms + 3 * static_cast<size_t>(termIndex);
+      out[0] = term.x;
+      out[1] = term.y;
+      out[2] = term.z;
       needItem = true;
     }
     __syncwarp();
@@ -395,6 +494,10 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
 
   if (!resident)
     stream.drain();
+  unsigned long long warpCasts = casts;
+#pragma unroll 1
+  for (int offset = 16; offset > 0; offset >>= 1)
+    warpCasts += __shfl_down_sync(kFullMask, warpCasts, offset);
   if (lane == 0 && warpCasts)
     atomicAdd(args.counters + 1, warpCasts);
 }
@@ -465,7 +568,8 @@ static cudaError_t launchPrimary(const SplitArgs &args, int numSms, cudaStream_t
 template <int kBlock, int kMinBlocks, int kSweep, bool kDeep>
 static cudaError_t launchSubPaths(const SplitArgs &args, int numSms, cudaStream_t stream) {
   auto kernel = subPathKernel<kBlock, kMinBlocks, kSweep, kDeep>;
-  const size_t smemBytes = smemAfterTiles(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep);
+  const size_t smemBytes = smemAfterTiles(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, kSweep) +
+                           static_cast<size_t>(kBlock) * kRecordQuads * sizeof(double2); // one Surface slot per thread
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes));
   if (err != cudaSuccess)
     return err;
@@ -501,7 +605,8 @@ static cudaError_t launchSplitShape(const SplitArgs &args, int numSms, cudaStrea
 }
 
 // A pipeline configuration is 100 + 10 * launchShape + sweepVariant (the megakernel's numbering
-// plus 100): sweep variants 1 (two-stage FP64) and 6 (sign-bit FP32 stage 0 + exact); launch
+// plus 100): sweep variants 1 (two-stage FP64), 6 (sign-bit FP32 stage 0 + exact) and 7 (the same in
+// moment form); launch
 // shapes of the sub-path kernel 0 = 256 threads x 2 CTAs/SM, 2 = 256 x 3, 3 = 192 x 4, 4 = 128 x 5,
 // 6 = 256 x 4.
 cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cudaStream_t stream) {
@@ -513,6 +618,10 @@ cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cud
   case 136: return launchSplitShape<192, 4, 6>(args, numSms, stream);
   case 146: return launchSplitShape<128, 5, 6>(args, numSms, stream);
   case 166: return launchSplitShape<256, 4, 6>(args, numSms, stream);
+  case 107: return launchSplitShape<256, 2, 7>(args, numSms, stream);
+  case 127: return launchSplitShape<256, 3, 7>(args, numSms, stream);
+  case 137: return launchSplitShape<192, 4, 7>(args, numSms, stream);
+  case 147: return launchSplitShape<128, 5, 7>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
 }

@@ -22,8 +22,9 @@ __host__ __device__ inline uint32_t smemTileOffset(uint32_t numSpheres) {
 
 constexpr uint32_t kExactBytesPerTriangle = 72;  // 9 doubles
 constexpr uint32_t kFilterBytesPerTriangle = 56; // 14 floats
+constexpr uint32_t kMomentBytesPerTriangle = 76; // 19 floats (sweep variant 7)
 __host__ __device__ inline uint32_t sweepBytesPerTriangle(int sweep) {
-  return sweep >= 2 ? kFilterBytesPerTriangle : kExactBytesPerTriangle;
+  return sweep == 7 ? kMomentBytesPerTriangle : sweep >= 2 ? kFilterBytesPerTriangle : kExactBytesPerTriangle;
 }
 
 __host__ __device__ inline uint32_t smemAfterTiles(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles,
@@ -88,7 +89,8 @@ struct TileStream {
 __device__ __forceinline__ TileStream makeTileStream(unsigned char *smemBase, const DeviceScene &scene,
                                                      int sweep) {
   return TileStream{smemBase,
-                    sweep >= 2 ? reinterpret_cast<const unsigned char *>(scene.triFilter)
+                    sweep == 7   ? reinterpret_cast<const unsigned char *>(scene.triMoment)
+                    : sweep >= 2 ? reinterpret_cast<const unsigned char *>(scene.triFilter)
                                : reinterpret_cast<const unsigned char *>(scene.triSweep),
                     scene.tileTris * sweepBytesPerTriangle(sweep), scene.numTiles,
                     smemTileOffset(scene.numSpheres), 0};
@@ -100,7 +102,10 @@ __device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const 
                                                 uint32_t tileIndex, V3 o, V3 d, Nearest &best) {
   const int tileTris = static_cast<int>(scene.tileTris);
   const int first = static_cast<int>(tileIndex * scene.tileTris);
-  if (kSweep >= 5)
+  if (kSweep == 7)
+    sweepTileStage0Moment<kFpWay>(reinterpret_cast<const float *>(tile), scene.triExact + static_cast<size_t>(first) * 10,
+                                  tileTris, first, o, d, best);
+  else if (kSweep >= 5)
     sweepTileStage0Signs<kSweep == 5, kFpWay>(reinterpret_cast<const float *>(tile),
                     scene.triExact + static_cast<size_t>(first) * 10, tileTris, first, o, d, best);
   else if (kSweep >= 2)

@@ -46,11 +46,12 @@ int fail(int code, const char *format, ...) {
       return fail(PTB200_ECUDA, "%s failed: %s", #call, cudaGetErrorString(ptErr_));             \
   } while (0)
 
-// Tile plan, in bytes of FP64 sweep data (72 B/triangle; the FP32 stage-0 tile is 56 B/triangle).
-// Budget: two CTAs per SM must fit in 227 KB, each with its tile buffer(s) plus 48 KB of
-// per-thread slots (primary hit + prefetched sample, 192 B x 256 threads).
-constexpr size_t kResidentTileBytes = 72 * 1024; // <= 1024 triangles: one resident tile per CTA
-constexpr size_t kStreamTileBytes = 40 * 1024;   // larger scenes: two buffers of <= 568 triangles
+// Tile plan.  Budget: two CTAs per SM must fit in 227 KB, each with its tile buffer(s) — up to
+// 76 B/triangle, the moment-form stage-0 data of sweep variant 7 — plus its per-thread slots
+// (36 KB of Surface slots in the sub-path kernel, 50 KB in the one-kernel form whose tiles are
+// 56 B/triangle).
+constexpr uint32_t kResidentTileTriangles = 976; // one resident tile per CTA up to here
+constexpr uint32_t kStreamTileTriangles = 480;   // larger scenes: two buffers of <= this
 constexpr size_t kSampleBufferBytes = size_t(4) << 30;
 // Keyed pipeline: records + strata terms of one batch of passes (pt_split.cu), ~530 B per sample
 // at 4x4 strata.  Batches of ~2 M samples keep the persistent sub-path kernel's tail below 1 %.
@@ -141,6 +142,7 @@ struct PtContext {
   DeviceBuffer<uint32_t> sphereMaterial;
   DeviceBuffer<double> materials;
   DeviceBuffer<float> triFilter;
+  DeviceBuffer<float> triMoment;
   DeviceBuffer<double> triExact;
   double sceneRadius{0};       // >= |p| for every vertex / sphere surface point
   double filterOriginBound{-1}; // origin bound the current triFilter contents were built for
@@ -211,10 +213,9 @@ void planTiles(uint32_t numTriangles, uint32_t &tileTris, uint32_t &numTiles) {
     numTiles = 0;
     return;
   }
-  const size_t bytes = static_cast<size_t>(numTriangles) * 72;
-  numTiles = bytes <= kResidentTileBytes
+  numTiles = numTriangles <= kResidentTileTriangles
                  ? 1u
-                 : static_cast<uint32_t>((bytes + kStreamTileBytes - 1) / kStreamTileBytes);
+                 : (numTriangles + kStreamTileTriangles - 1) / kStreamTileTriangles;
   tileTris = (numTriangles + numTiles - 1) / numTiles;
   tileTris = (tileTris + 3u) & ~3u; // 16-byte loads of 2 doubles / 4 floats
   numTiles = (numTriangles + tileTris - 1) / tileTris;
@@ -374,6 +375,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   PT_CUDA(ctx->triSweep.ensure(sweepDoubles));
   PT_CUDA(ctx->triShade.ensure(shade.size()));
   PT_CUDA(ctx->triFilter.ensure(static_cast<size_t>(d.numTiles) * 14 * d.tileTris));
+  PT_CUDA(ctx->triMoment.ensure(static_cast<size_t>(d.numTiles) * 19 * d.tileTris));
   PT_CUDA(ctx->triExact.ensure(exact.size()));
   PT_CUDA(ctx->spheres.ensure(spheres.size()));
   PT_CUDA(ctx->sphereMaterial.ensure(scene->numSpheres));
@@ -402,6 +404,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   d.sphereMaterial = ctx->sphereMaterial.ptr;
   d.materials = ctx->materials.ptr;
   d.triFilter = ctx->triFilter.ptr;
+  d.triMoment = ctx->triMoment.ptr;
   d.triExact = ctx->triExact.ptr;
   d.environment[0] = scene->environment[0];
   d.environment[1] = scene->environment[1];
@@ -419,6 +422,7 @@ static int ensureFilter(PtContext *ctx, double originBound, uint64_t *launches) 
   BuildFilterArgs b{};
   b.scene = ctx->scene;
   b.out = ctx->triFilter.ptr;
+  b.outMoment = ctx->triMoment.ptr;
   b.originBound = originBound;
   PT_CUDA(launchBuildFilter(b, ctx->stream));
   ctx->filterOriginBound = originBound;
@@ -454,12 +458,12 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
   const size_t pixelsPerPass = sequential ? static_cast<size_t>(params->width) * params->height : ownPixels;
   size_t passesPerBatch;
   if (split) {
-    if (numSub * ownPixels >= (uint64_t(1) << 32))
+    if (numSub * ownPixels >= (uint64_t(1) << 31))
       return fail(PTB200_EINVAL, "%llu strata x %u pixels exceed the sub-path index range",
                   static_cast<unsigned long long>(numSub), ownPixels);
     const size_t perSample = splitBytesPerSample(static_cast<uint32_t>(numSub));
     passesPerBatch = std::max<size_t>(1, kSplitBufferBytes / (pixelsPerPass * perSample));
-    passesPerBatch = std::min<size_t>(passesPerBatch, ((uint64_t(1) << 32) - 1) / (numSub * ownPixels));
+    passesPerBatch = std::min<size_t>(passesPerBatch, ((uint64_t(1) << 31) - 1) / (numSub * ownPixels));
   } else {
     passesPerBatch = std::max<size_t>(1, kSampleBufferBytes / (pixelsPerPass * 24));
   }
@@ -535,6 +539,10 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.totalSamples = ownPixels * static_cast<uint32_t>(batch);
       a.numPasses = static_cast<uint32_t>(batch);
       a.numSub = static_cast<uint32_t>(numSub);
+      a.numSubShift = (numSub & (numSub - 1)) == 0 ? __builtin_ctzll(numSub) : -1;
+      a.firstBounceVShift = (params->firstBounceVSamples & (params->firstBounceVSamples - 1)) == 0
+                                ? __builtin_ctz(static_cast<unsigned>(params->firstBounceVSamples))
+                                : -1;
       a.numMaterials = ctx->numMaterials;
       a.seed = params->seed;
       a.passBegin = passBegin + done;
@@ -683,6 +691,24 @@ int ptb200_context_download(PtContext *ctx, PtPixel *out) {
   return PTB200_OK;
 }
 
+// D2H of the rows a row-partitioned call rendered (every row when the call was not partitioned):
+// one strided copy, rows y = rowBegin + k * rowStep; the other rows of `out` are not written.
+static int downloadRows(PtContext *ctx, PtPixel *out, const PtRenderOptions *options) {
+  if (!ctx->accumulator.ptr || ctx->accWidth == 0)
+    return fail(PTB200_ESTATE, "nothing rendered yet");
+  const int rowStep = options && options->rowStep > 0 ? options->rowStep : 1;
+  const int rowBegin = options ? options->rowBegin : 0;
+  if (rowBegin >= ctx->accHeight)
+    return PTB200_OK;
+  const size_t rowBytes = static_cast<size_t>(ctx->accWidth) * sizeof(PtPixel);
+  const size_t ownRows = static_cast<size_t>((ctx->accHeight - rowBegin + rowStep - 1) / rowStep);
+  const size_t first = static_cast<size_t>(rowBegin) * ctx->accWidth;
+  PT_CUDA(cudaMemcpy2DAsync(out + first, rowBytes * rowStep, ctx->accumulator.ptr + first, rowBytes * rowStep,
+                            rowBytes, ownRows, cudaMemcpyDeviceToHost, ctx->stream));
+  PT_CUDA(cudaStreamSynchronize(ctx->stream));
+  return PTB200_OK;
+}
+
 int ptb200_render(const PtScene *scene, const PtCamera *camera, const PtRenderParams *params,
                   const PtRenderOptions *options, PtPixel *out, PtProgressFn progress, void *user,
                   PtStats *stats) {
@@ -701,14 +727,22 @@ int ptb200_render(const PtScene *scene, const PtCamera *camera, const PtRenderPa
   rc = ptb200_context_upload_scene(ctx, scene);
   PtStats total{};
   if (rc == PTB200_OK) {
-    if (!progress) {
+    if (!progress || params->samplesPerPixel == 0) {
+      // (spp == 0 still sizes and zeroes the accumulator: the download below must not see the
+      // previous call's frame of a pooled context)
       rc = ptb200_context_render(ctx, camera, params, options, 0, &total);
     } else {
       // Progressive: render in slices of passes, handing the partial framebuffer to the
       // caller on this thread between slices (Scene.cpp:242-245 does so per collected pass).
       PtRenderOptions slice = options ? *options : PtRenderOptions{};
       const int spp = params->samplesPerPixel;
-      const int step = slice.passesPerBatch > 0 ? slice.passesPerBatch : std::max(1, (spp + 19) / 20);
+      const bool passParallelOnly = slice.rngMode == PTB200_RNG_MT19937_SEQUENTIAL ||
+                                    slice.rngMode == PTB200_RNG_MT19937_SEQUENTIAL_OO;
+      // The sequential stream modes are parallel over passes only (one warp per pass): slicing
+      // them would leave the device idle, so they render in one slice unless the caller asks.
+      const int step = slice.passesPerBatch > 0 ? slice.passesPerBatch
+                       : passParallelOnly       ? spp
+                                                : std::max(1, (spp + 19) / 20);
       const int firstPass = slice.passBegin;
       for (int done = 0; done < spp && rc == PTB200_OK;) {
         PtRenderParams part = *params;
@@ -724,14 +758,17 @@ int ptb200_render(const PtScene *scene, const PtCamera *camera, const PtRenderPa
         total.kernelMs += one.kernelMs;
         total.sweepKernelMs += one.sweepKernelMs;
         done += part.samplesPerPixel;
-        rc = ptb200_context_download(ctx, out);
+        rc = downloadRows(ctx, out, options);
         if (rc == PTB200_OK && progress(user, out, done, spp) != 0)
           break;
       }
     }
   }
+  if (rc == PTB200_OK && (ctx->accWidth != params->width || ctx->accHeight != params->height))
+    rc = fail(PTB200_ESTATE, "accumulator is %dx%d, expected %dx%d", ctx->accWidth, ctx->accHeight,
+              params->width, params->height);
   if (rc == PTB200_OK)
-    rc = ptb200_context_download(ctx, out);
+    rc = downloadRows(ctx, out, options);
   if (rc == PTB200_OK)
     poolGive(ctx);
   else
@@ -834,7 +871,8 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
   // Test hooks in `which`: bit 8 = the warp-cooperative sweep of the sequential kernel;
   // bits 9-11 = per-lane sweep variant + 1 (0 -> default two-stage FP64); bit 12 = stage-0
   // audit: `out` then receives four uint64 counters (pairs, stage-0 survivors, exact accepts,
-  // VIOLATIONS) instead of hits.
+  // VIOLATIONS) instead of hits; bit 13 = audit the moment-form filter (variant 7); bit 14 = bit 3
+  // of the sweep-variant field.
   const int32_t mode = which & 0xff;
   if (mode < 0 || mode > 2)
     return fail(PTB200_EINVAL, "which must be 0, 1 or 2");
@@ -861,7 +899,7 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
     a.which = mode;
     a.nearerThan = nearerThan;
     a.warpCooperative = (which & 0x100) ? 1 : 0;
-    const int variant = (which >> 9) & 7;
+    const int variant = ((which >> 9) & 7) | ((which >> 11) & 8); // bit 14 extends the field
     a.sweep = variant ? variant - 1 : 1;
     const bool audit = (which & 0x1000) != 0;
     if (a.sweep >= 2 || audit) {
@@ -882,6 +920,7 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
       au.scene = ctx->scene;
       au.rays = dRays.ptr;
       au.numRays = numRays;
+      au.momentForm = (which & 0x2000) ? 1 : 0;
       au.counters = counters.ptr;
       PT_CUDA(launchAuditStage0(au, ctx->stream));
       PT_CUDA(cudaMemcpyAsync(out, counters.ptr, 32, cudaMemcpyDeviceToHost, ctx->stream));

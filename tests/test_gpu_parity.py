@@ -54,7 +54,7 @@ def assert_hits_equal(got, want):
 
 @pytest.mark.parametrize("name", SCENE_NAMES)
 @pytest.mark.parametrize("sweep", ["two-stage", "one-stage", "fp32-stage0", "fp32x2-stage0", "fp32x2-stage0-t",
-                                   "fp32x2-signs-t", "fp32x2-signs", "warp-cooperative"])
+                                   "fp32x2-signs-t", "fp32x2-signs", "fp32x2-moment", "warp-cooperative"])
 def test_intersect_matches_oracle(name, sweep, scenes, oracle, capi):
     """Every sweep implementation (two-stage FP64 prefilter + exact, plain one-stage, FP32 stage 0 +
     exact, the sequential kernel's lane-strided sweep) returns the oracle's nearest hit bit for bit."""
@@ -64,7 +64,7 @@ def test_intersect_matches_oracle(name, sweep, scenes, oracle, capi):
     variant = {"two-stage": capi.SWEEP_TWO_STAGE_FP64, "one-stage": capi.SWEEP_ONE_STAGE,
                "fp32-stage0": capi.SWEEP_FP32_STAGE0, "fp32x2-stage0": capi.SWEEP_FP32X2_STAGE0,
                "fp32x2-stage0-t": capi.SWEEP_FP32X2_STAGE0_T, "fp32x2-signs-t": capi.SWEEP_FP32X2_SIGNS_T,
-               "fp32x2-signs": capi.SWEEP_FP32X2_SIGNS}.get(sweep)
+               "fp32x2-signs": capi.SWEEP_FP32X2_SIGNS, "fp32x2-moment": capi.SWEEP_FP32X2_MOMENT}.get(sweep)
     got = capi.intersect(scene, rays, warp_cooperative=sweep == "warp-cooperative", sweep=variant)
     assert (want[:, 0] != 0).sum() > 100
     assert_hits_equal(got, want)
@@ -81,11 +81,12 @@ def test_fp32_stage0_never_rejects_an_exact_hit(name, scenes, capi):
     tri = scene.triangle_vertices[np.random.default_rng(5).integers(0, scene.num_triangles, n // 4)].reshape(-1, 3, 3)
     inplane = tri[:, 1] - tri[:, 0] + 1e-7 * (tri[:, 2] - tri[:, 0])
     rays[: n // 4, 3:] = inplane / np.linalg.norm(inplane, axis=1, keepdims=True)
-    res = capi.audit_stage0(scene, rays)
-    assert res["pairs"] == n * scene.num_triangles
-    assert res["violations"] == 0
-    assert res["accepts"] > 0 and res["survivors"] >= res["accepts"]
-    assert res["survivors"] < 0.5 * res["pairs"]
+    for moment_form in (False, True):  # the classic FP32 form (variants 2-6) and the moment form (7)
+        res = capi.audit_stage0(scene, rays, moment_form=moment_form)
+        assert res["pairs"] == n * scene.num_triangles
+        assert res["violations"] == 0
+        assert res["accepts"] > 0 and res["survivors"] >= res["accepts"]
+        assert res["survivors"] < 0.5 * res["pairs"]
 
 
 @pytest.mark.parametrize("which", [1, 2])
@@ -250,7 +251,7 @@ def test_every_megakernel_configuration_renders_identically(scene_name, w, h, sc
                 root, os.path.join(root, "tests/golden/scenes/%s.ptscene" % scene_name), w, h, w, h)
     outs = []
     for config in ("1", "0", "2", "3", "4", "13", "24", "43", "5", "6", "25", "26", "35", "46", "56",
-                   "101", "106", "121", "126", "136", "146", "166"):
+                   "101", "106", "121", "126", "136", "146", "166", "107", "127", "137", "147"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
@@ -311,11 +312,12 @@ def test_random_scene_intersections_match_oracle(seed, oracle, capi):
     want = oracle.OracleScene(scene).intersect(rays)
     for sweep in (capi.SWEEP_ONE_STAGE, capi.SWEEP_TWO_STAGE_FP64, capi.SWEEP_FP32_STAGE0,
                   capi.SWEEP_FP32X2_STAGE0, capi.SWEEP_FP32X2_STAGE0_T, capi.SWEEP_FP32X2_SIGNS_T,
-                  capi.SWEEP_FP32X2_SIGNS):
+                  capi.SWEEP_FP32X2_SIGNS, capi.SWEEP_FP32X2_MOMENT):
         assert_hits_equal(capi.intersect(scene, rays, sweep=sweep), want)
     assert_hits_equal(capi.intersect(scene, rays, warp_cooperative=True), want)
-    audit = capi.audit_stage0(scene, rays)
-    assert audit["violations"] == 0 and audit["accepts"] > 0
+    for moment_form in (False, True):
+        audit = capi.audit_stage0(scene, rays, moment_form=moment_form)
+        assert audit["violations"] == 0 and audit["accepts"] > 0
 
 
 @pytest.mark.parametrize("mode_name", ["keyed", "sequential"])

@@ -69,6 +69,23 @@ def test_unmodified_render_entry_point_sums_passes(ref, tmp_path):
     assert np.abs(got["sums"] - sums).max() <= 1e-10 * max(1.0, float(np.abs(sums).max()))
 
 
+def test_every_pass_kept_driver_equals_the_oracle(ref, tmp_path):
+    """`ref_tool passes` (bench.py's CPU baseline: the reference's radiance()/randomRay() for every
+    pass, fairly scheduled over threads, nothing dropped) renders the oracle's image: spp samples
+    everywhere, sums equal up to the thread-dependent order of `+=` over passes."""
+    scene = random_scenes.random_scene(7, num_triangles=12, num_spheres=2)
+    path = str(tmp_path / "scene.ptscene")
+    scenefile.save(scene, path)
+    out = str(tmp_path / "passes.raw")
+    info = ref.ref_passes(path, 16, 16, 6, 3, 3, out)
+    assert info["total_samples"] == 16 * 16 * 6
+    sums, counts = ref.read_raw(out)
+    assert (counts == 6).all()
+    got = ref.OracleScene(scene).render(scene.camera(16, 16), ref.params_array(16, 16, spp=6, seed=3),
+                                        ref.RNG_MT19937_SEQUENTIAL)
+    assert np.abs(got["sums"] - sums).max() <= 1e-10 * max(1.0, float(np.abs(sums).max()))
+
+
 @pytest.mark.parametrize("seed,kw", [(4, {}), (5, dict(first_u=3, first_v=2, max_depth=7)), (6, dict(max_depth=2)),
                                      (8, dict(first_u=1, first_v=5, max_depth=9)),
                                      (9, dict(first_u=8, first_v=8, max_depth=6))])

@@ -4,7 +4,8 @@ stage0Reject2, bounds built by buildFilterKernel in csrc/pt_kernels.cu), restate
 * soundness: a triangle the reference's FP64 Moller-Trumbore accepts (Scene.cpp:62-98, with no
   nearer-than limit) is never rejected by the FP32 filter with its per-triangle error bounds;
 * the sign-bit formulation (variants 5/6: sign of (a|b|c|e) & f) takes exactly the decisions of
-  the comparison formulation (variants 3/4).
+  the comparison formulation (variants 3/4);
+* the moment (Pluecker) form of variant 7 (stage0RejectMoment) is sound under the same bounds.
 
 float32 FMAs are emulated as float64 products/sums rounded once to float32 (products of two
 float32 values are exact in float64; the sum adds one double rounding the GPU does not have, far
@@ -71,6 +72,34 @@ def stage0(v0, e1, e2, o, d, origin_bound):
     return keep_cmp, keep_sign, keep_cmp_t, keep_sign_t
 
 
+def stage0_moment(v0, e1, e2, o, d, origin_bound):
+    """Sweep variant 7 (stage0RejectMoment): det, X, Y as dot products of the ray's (d, m = o x d)
+    with per-triangle constants evaluated in float64 and rounded once; the bounds and the sign-bit
+    decision are the classic form's."""
+    ed, kx, ky, k3, _ = bounds(v0, e1, e2, origin_bound)
+    nn, a2, a1 = np.cross(e2, e1), np.cross(v0, e2), np.cross(v0, e1)
+    m = np.cross(o, d)
+    nn, e2f, a2, f1, b1, m, d = (a.astype(F) for a in (nn, e2, a2, -e1, -a1, m, d))
+    X, Y, Z = 0, 1, 2
+    det = fma32(d[:, Z], nn[:, Z], fma32(d[:, Y], nn[:, Y], mul32(d[:, X], nn[:, X])))
+
+    def six(p, q):  # p . m + q . d in the kernel's operation order
+        acc = fma32(m[:, Y], p[:, Y], mul32(m[:, X], p[:, X]))
+        acc = fma32(m[:, Z], p[:, Z], acc)
+        acc = fma32(d[:, X], q[:, X], acc)
+        acc = fma32(d[:, Y], q[:, Y], acc)
+        return fma32(d[:, Z], q[:, Z], acc)
+
+    x, y = six(e2f, a2), six(f1, b1)
+    s = np.where(np.signbit(det), F(-1), F(1))
+    adet = np.abs(det)
+    bound = fma32(adet, np.full_like(adet, F(1) + F(2.0 ** -20)), k3)
+    a, b = fma32(x, s, kx), fma32(y, s, ky)
+    e = fma32(-(x + y).astype(F), s, bound)
+    f = (ed - adet).astype(F)
+    return ~((np.signbit(a) | np.signbit(b) | np.signbit(e)) & np.signbit(f))
+
+
 def exact_accepts(v0, e1, e2, o, d):
     """testTriangle with best.t = +inf: the reference's arithmetic in float64 (numpy has no FMA;
     a last-bit difference in u, v or t only matters within ~1e-16 of an edge)."""
@@ -120,8 +149,12 @@ def test_fp32_stage0_bounds_never_reject_an_exact_hit(scale):
     accepts = exact_accepts(v0, e1, e2, o, d)
     assert accepts.sum() > 100_000          # the aimed rays do hit
     assert (~keep_cmp).sum() > 50_000       # ... and the filter does reject the others
-    for keep in (keep_cmp, keep_sign, keep_cmp_t, keep_sign_t):
+    keep_moment = stage0_moment(v0, e1, e2, o, d, origin_bound)
+    assert (~keep_moment).sum() > 50_000
+    for keep in (keep_cmp, keep_sign, keep_cmp_t, keep_sign_t, keep_moment):
         assert not (accepts & ~keep).any()  # soundness
+    # the moment form is (slightly) the tighter filter: its rounding errors are about half
+    assert keep_moment.sum() <= keep_sign.sum() * 1.001
 
 
 @pytest.mark.parametrize("scale", [1.0, 30.0])
