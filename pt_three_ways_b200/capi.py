@@ -171,13 +171,18 @@ def _stats_dict(st: PtStats) -> dict:
 
 
 def render(scene, camera18, params: PtRenderParams, options: PtRenderOptions | None = None,
-           progress=None, devices=None):
+           progress=None, devices=None, out=None):
     """One-shot host-buffer render through ptb200_render (or ptb200_render_multi when
-    `devices` is a list / "all").  Returns (pixels structured array (H,W), stats dict)."""
+    `devices` is a list / "all").  Returns (pixels structured array (H,W), stats dict).
+    `out`: an existing C-contiguous (H,W) PIXEL_DTYPE array to render into (e.g. a frame shared
+    between ranks: a row-partitioned call writes only its own rows)."""
     m = scene if isinstance(scene, MarshalledScene) else MarshalledScene(scene)
     cam = make_camera(camera18)
     opts = options or make_options()
-    out = np.zeros((params.height, params.width), dtype=PIXEL_DTYPE)
+    if out is None:
+        out = np.zeros((params.height, params.width), dtype=PIXEL_DTYPE)
+    elif out.shape != (params.height, params.width) or out.dtype != PIXEL_DTYPE or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous (height, width) PIXEL_DTYPE array")
     st = PtStats()
     if devices is not None:
         if devices == "all":

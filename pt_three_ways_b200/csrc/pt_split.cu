@@ -622,6 +622,9 @@ cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cud
   case 127: return launchSplitShape<256, 3, 7>(args, numSms, stream);
   case 137: return launchSplitShape<192, 4, 7>(args, numSms, stream);
   case 147: return launchSplitShape<128, 5, 7>(args, numSms, stream);
+  case 167: return launchSplitShape<256, 4, 7>(args, numSms, stream);
+  case 177: return launchSplitShape<224, 4, 7>(args, numSms, stream);
+  case 187: return launchSplitShape<128, 6, 7>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
 }

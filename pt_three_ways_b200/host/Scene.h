@@ -22,6 +22,7 @@
 #include <optional>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace ptb200 {
@@ -54,6 +55,7 @@ class Scene {
   PtRenderOptions options_{};
   PtStats lastStats_{};
   bool useAllDevices_{false};
+  std::vector<int32_t> deviceList_; // explicit devices of a multi-GPU render (empty: options_.device)
 
   uint32_t intern(const MaterialSpec &material) {
     for (size_t i = palette_.size(); i-- > 0;) // recently used materials are at the back
@@ -126,7 +128,9 @@ public:
   // --- backend knobs (no reference equivalent) -------------------------------------------
   void setRngMode(int mode) { options_.rngMode = mode; }
   void setDevice(int device) { options_.device = device; }
-  void setUseAllDevices(bool all) { useAllDevices_ = all; }
+  void setUseAllDevices(bool all) { useAllDevices_ = all; deviceList_.clear(); }
+  // Render on exactly these CUDA ordinals (row-partitioned framebuffer, ptb200_render_multi).
+  void setDevices(std::vector<int32_t> devices) { deviceList_ = std::move(devices); useAllDevices_ = false; }
   void setPassesPerBatch(int passes) { options_.passesPerBatch = passes; }
   [[nodiscard]] const PtStats &lastStats() const noexcept { return lastStats_; }
   [[nodiscard]] size_t numTriangles() const noexcept { return triangleMaterial_.size(); }
@@ -168,9 +172,11 @@ public:
       return 0;
     };
 
-    if (useAllDevices_) {
-      check(ptb200_render_multi(&m.scene, &camera.abi(), &params, &options_, nullptr, 0,
-                                raw.data(), &lastStats_),
+    const bool multi = useAllDevices_ || deviceList_.size() > 1;
+    if (multi) {
+      check(ptb200_render_multi(&m.scene, &camera.abi(), &params, &options_,
+                                deviceList_.empty() ? nullptr : deviceList_.data(),
+                                static_cast<int32_t>(deviceList_.size()), raw.data(), &lastStats_),
             "ptb200_render_multi");
     } else {
       check(ptb200_render(&m.scene, &camera.abi(), &params, &options_, raw.data(),
@@ -179,7 +185,7 @@ public:
     }
     ArrayOutput output(renderParams.width, renderParams.height);
     output.addSamples(raw.data());
-    if (updateFunc && useAllDevices_)
+    if (updateFunc && multi)
       updateFunc(output);
     return output;
   }

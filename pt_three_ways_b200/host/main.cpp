@@ -20,6 +20,7 @@
 #include <iostream>
 #include <random>
 #include <string>
+#include <vector>
 
 using namespace ptb200;
 
@@ -92,7 +93,10 @@ int usage(const char *argv0) {
             << " [-w W] [-h H] [--spp N] [--max-cpus N] [--first-bounce-u N] [--first-bounce-v N]\n"
                "       [--max-depth N] [--seed N] [--preview] [--save-every SECS] [--way dod|fp|oo]\n"
                "       [--scene NAME] [--raw] [--rng keyed|exact] [--gpus N] [--device K]\n"
-               "       [--scenes DIR] <output>\n";
+               "       [--scenes DIR] [--ptscene FILE] <output>\n"
+               "       --merge <a.raw> <b.raw>... [--raw] <output>   (sum framebuffers instead of rendering)\n"
+               "  --way dod (the default here; the reference's default is oo) renders the dod estimator with\n"
+               "  --rng keyed (default) or exact; --gpus N uses devices [--device, --device + N), 0 = all.\n";
   return 1;
 }
 
@@ -110,6 +114,7 @@ int main(int argc, const char *argv[]) {
   std::string rng = "keyed";
   std::string ptsceneFile;
   std::string outputName;
+  std::vector<std::string> mergeInputs; // --merge: sum raw framebuffers instead of rendering
 
   for (int i = 1; i < argc; ++i) {
     const std::string arg = argv[i];
@@ -138,6 +143,10 @@ int main(int argc, const char *argv[]) {
     else if (arg == "--device") device = std::stoi(value());
     else if (arg == "--scenes") scenesDir = value();
     else if (arg == "--ptscene") ptsceneFile = value();
+    else if (arg == "--merge") {
+      while (i + 1 < argc && std::string(argv[i + 1]).rfind("--", 0) != 0 && i + 2 < argc)
+        mergeInputs.push_back(argv[++i]); // every following name but the last one (the output)
+    }
     else if (arg == "--help" || arg == "-?") return usage(argv[0]);
     else if (!arg.empty() && arg[0] == '-') {
       std::cerr << "Error in command line: unknown option " << arg << '\n';
@@ -155,6 +164,15 @@ int main(int argc, const char *argv[]) {
     std::cerr << "Unknown way " << way << "\n"; // main.cpp:365
     return 1;
   }
+  if (rng != "keyed" && rng != "exact") {
+    std::cerr << "Unknown rng " << rng << " (keyed: counter-based Philox, parallel over pixels; exact: the "
+                 "reference's mt19937 stream, parallel over passes)\n";
+    return 1;
+  }
+  if (gpus < 0) {
+    std::cerr << "Error in command line: --gpus must be 0 (all devices) or a positive count\n";
+    return 1;
+  }
   if (renderParams.seed == 0) { // main.cpp:426-429
     std::random_device rd;
     renderParams.seed = static_cast<int>(rd());
@@ -165,6 +183,27 @@ int main(int argc, const char *argv[]) {
     save = [outputName](const ArrayOutput &output) { output.save(outputName); };
   else
     save = [outputName](const ArrayOutput &output) { savePng(output, outputName); };
+
+  if (!mergeInputs.empty()) {
+    // Partial renders (other seeds, GPUs, machines; the reference's own --raw files included)
+    // are summed pixel by pixel — what the reference's raw_to_png tool does with
+    // ArrayOutput::load and operator+= (src/main/raw_to_png.cpp:39-59) — and written as PNG or,
+    // with --raw, as one raw file again.
+    try {
+      ArrayOutput merged = ArrayOutput::load(mergeInputs.front());
+      for (size_t k = 1; k < mergeInputs.size(); ++k)
+        merged += ArrayOutput::load(mergeInputs[k]); // throws std::logic_error on a size mismatch
+      const double perPixel = static_cast<double>(merged.totalSamples()) /
+                              (static_cast<double>(merged.width()) * static_cast<double>(merged.height()));
+      std::cout << "Merged " << mergeInputs.size() << " framebuffers of " << merged.width() << "x" << merged.height()
+                << ": " << merged.totalSamples() << " samples, " << perPixel << " per pixel\n";
+      save(merged);
+    } catch (const std::exception &e) {
+      std::cerr << "Error: " << e.what() << '\n';
+      return 1;
+    }
+    return 0;
+  }
 
   try {
     using namespace std::chrono_literals;
@@ -197,7 +236,14 @@ int main(int argc, const char *argv[]) {
                      : way == "oo" ? PTB200_RNG_MT19937_SEQUENTIAL_OO
                      : rng == "exact" ? PTB200_RNG_MT19937_SEQUENTIAL : PTB200_RNG_KEYED_PHILOX);
     scene.setDevice(device);
-    scene.setUseAllDevices(gpus != 1);
+    if (gpus == 0) { // every visible device
+      scene.setUseAllDevices(true);
+    } else if (gpus > 1) { // devices [device, device + gpus)
+      std::vector<int32_t> devices;
+      for (int g = 0; g < gpus; ++g)
+        devices.push_back(device + g);
+      scene.setDevices(devices);
+    }
 
     const auto start = std::chrono::system_clock::now();
     ArrayOutput output = scene.render(camera, renderParams, throttledSave);

@@ -50,3 +50,37 @@ def gather_rows(local_frame: np.ndarray, rank: int, world: int, group=None, dst:
         scatter_rows(frame, rows[:n], r, world)
     assert item == frame.dtype.itemsize
     return frame
+
+
+class SharedFrame:
+    """The final gather without a copy: ONE framebuffer in host shared memory (/dev/shm) mapped by
+    every rank of the box.  Each rank's row-partitioned render writes its own rows y = rank (mod N)
+    straight into it (ptb200_render's D2H is a strided copy of exactly those rows), so after a
+    barrier rank 0 holds the assembled frame — the host-side analogue of `output += pass`
+    (src/dod/Scene.cpp:242) for disjoint rows.  No collective touches pixel data."""
+
+    def __init__(self, height: int, width: int, dtype, tag: str, rank: int, barrier=None):
+        import os
+        self.path = os.path.join("/dev/shm" if os.path.isdir("/dev/shm") else "/tmp", f"ptb200_frame_{tag}.bin")
+        self.rank, self.barrier = rank, barrier or (lambda: None)
+        nbytes = height * width * np.dtype(dtype).itemsize
+        if rank == 0:
+            with open(self.path, "wb") as f:
+                f.truncate(nbytes)
+        self.barrier()
+        self.frame = np.memmap(self.path, dtype=dtype, mode="r+", shape=(height, width))
+
+    def gathered(self):
+        """Call on every rank after its render into `self.frame`; returns the frame on rank 0."""
+        self.barrier()
+        return self.frame if self.rank == 0 else None
+
+    def close(self):
+        import os
+        self.barrier()
+        del self.frame
+        if self.rank == 0:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass

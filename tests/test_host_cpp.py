@@ -55,20 +55,20 @@ def test_cli_accepts_every_way_and_has_no_cpu_fallback(tmp_path):
         assert not (tmp_path / "out.raw").exists()
 
 
-def test_raw_to_png_merges_like_the_reference_tool(tmp_path):
-    """raw_to_png_b200 out.png a.raw b.raw: sizes and sample totals are reported, the sum is
-    saved as a valid PNG; the reference's own raw file (tests/golden) is accepted as input."""
+def test_merge_mode_sums_raw_framebuffers(tmp_path):
+    """pt_b200 --merge a.raw b.raw out.png (what the reference's raw_to_png tool is for,
+    src/main/raw_to_png.cpp:39-59): the sum is saved as a valid PNG or, with --raw, as a raw file
+    again; the reference's own raw file (tests/golden) is accepted as input."""
     import struct
     import zlib
     import numpy as np
-    exe = os.path.join(HOST, "raw_to_png_b200")
+    exe = os.path.join(HOST, "pt_b200")
     subprocess.run(["make", "-C", HOST], check=True, capture_output=True)
     golden = os.path.join(ROOT, "tests", "golden", "render_asis_cornell.raw")
     out = str(tmp_path / "merged.png")
-    res = subprocess.run([exe, out, golden, golden], capture_output=True, text=True)
+    res = subprocess.run([exe, "--merge", golden, golden, out], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
-    assert "width: 16 height: 16" in res.stdout and "samples: 3840" in res.stdout
-    assert "with 7680 samples (30.0 per pixel)" in res.stdout
+    assert "Merged 2 framebuffers of 16x16: 7680 samples, 30 per pixel" in res.stdout
     data = open(out, "rb").read()
     assert data[:8] == b"\x89PNG\r\n\x1a\n"
     w, h = struct.unpack(">II", data[16:24])
@@ -87,5 +87,11 @@ def test_raw_to_png_merges_like_the_reference_tool(tmp_path):
     mean = sums / counts[..., None]  # doubling sums and counts leaves the mean unchanged
     want = np.round(np.clip(mean, 0, 1) ** (1 / 2.2) * 255).astype(np.uint8)
     assert np.abs(rows[:, 1:].reshape(16, 16, 3).astype(int) - want.astype(int)).max() <= 1
-    res = subprocess.run([exe, out], capture_output=True, text=True)
-    assert res.returncode == 1 and "Missing inputs" in res.stderr
+    # --raw: the merged framebuffer in the reference's raw format, sums and counts doubled
+    raw_out = str(tmp_path / "merged.raw")
+    res = subprocess.run([exe, "--merge", golden, golden, "--raw", raw_out], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    sums2, counts2 = ob.read_raw(raw_out)
+    assert np.array_equal(sums2, sums + sums) and np.array_equal(counts2, counts * 2)
+    res = subprocess.run([exe, "--merge", golden, str(tmp_path / "missing.raw"), out], capture_output=True, text=True)
+    assert res.returncode == 1 and "Error" in res.stderr

@@ -31,6 +31,13 @@ local["n"] = res["counts"]
 frame = partition.gather_rows(local, rank, world)
 if rank == 0:
     np.save(%(out)r, frame)
+# the copy-free gather bench.py uses: every rank's rows land in ONE shared host frame
+shared = partition.SharedFrame(h, w, capi.PIXEL_DTYPE, "gloo_test_%%d" %% os.getppid(), rank, dist.barrier)
+shared.frame[rank::world] = local[rank::world]   # what ptb200_render's strided D2H does
+assembled = shared.gathered()
+if rank == 0:
+    np.save(%(out)r + ".shared.npy", np.array(assembled))
+shared.close()
 dist.barrier()
 dist.destroy_process_group()
 """
@@ -57,6 +64,8 @@ def test_two_rank_row_partition_and_host_gather(tmp_path, scenes, oracle, capi):
                                              oracle.RNG_KEYED_PHILOX)
     assert np.array_equal(frame["sum"], whole["sums"])
     assert np.array_equal(frame["n"], whole["counts"])
+    shared = np.load(out + ".shared.npy")
+    assert np.array_equal(shared["sum"], whole["sums"]) and np.array_equal(shared["n"], whole["counts"])
 
 
 def test_rows_of_rank_cover_the_frame_once():

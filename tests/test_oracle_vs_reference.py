@@ -147,3 +147,40 @@ def test_oo_way_unmodified_render_entry_point(ref, tmp_path):
     got = ref.OracleScene(scene).render(scene.camera(16, 16), ref.params_array(16, 16, spp=kept, seed=3),
                                         ref.RNG_OO_SEQUENTIAL)
     assert np.abs(got["sums"] - sums).max() <= 1e-10 * max(1.0, float(np.abs(sums).max()))
+
+
+@pytest.mark.parametrize("name", ["cornell", "suzanne", "ce", "single-sphere", "multi-sphere", "example1", "bbc-owl"])
+def test_dropin_adaptor_marshals_what_the_reference_recipes_build(name, tmp_path, scenes):
+    """CPU half of the drop-in proof (the GPU half is tests/test_gpu_parity_at_size.py):
+    include/ptb200_scene.hpp compiled against the reference's own types, fed by the reference's own
+    createScene<SB> + loadObjFile, hands the C ABI exactly the arrays of the committed fixture —
+    triangles, spheres, per-primitive materials, environment and the 18 camera doubles."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "b200_dropin")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("oracle/_ref/b200_dropin not built (needs /root/reference)")
+    out = str(tmp_path / "arrays.bin")
+    res = subprocess.run([exe, "arrays", name, "640", "480", out], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stderr
+    data = open(out, "rb").read()
+    t, s, m, _ = np.frombuffer(data, dtype="<u4", count=4)
+    off = 16
+    def take(dtype, count):
+        nonlocal off
+        arr = np.frombuffer(data, dtype=dtype, count=count, offset=off)
+        off += arr.nbytes
+        return arr
+    env = take("<f8", 3)
+    tri = take("<f8", int(t) * 9).reshape(-1, 9)
+    tri_mat = take("<u4", int(t))
+    sph = take("<f8", int(s) * 4).reshape(-1, 4)
+    sph_mat = take("<u4", int(s))
+    mats = take("<f8", int(m) * 9).reshape(-1, 9)
+    cam = take("<f8", 18)
+    want = scenes[name]
+    assert np.array_equal(tri, want.triangle_vertices) and np.array_equal(sph, want.sphere_centre_radius)
+    assert np.array_equal(env, want.environment)
+    assert np.array_equal(mats[tri_mat], want.materials[want.triangle_material])
+    assert np.array_equal(mats[sph_mat], want.materials[want.sphere_material])
+    assert np.array_equal(cam, want.camera(640, 480))

@@ -23,14 +23,22 @@ def num(x):
 
 
 def launch_shares(path):
+    """Per kernel: launches, total time and share; DRAM bytes when the list carries those metrics
+    (one CSV row per launch and metric: ..., metric name, unit, value)."""
     rows = [r for r in csv.reader(open(path)) if len(r) > 10 and r[0].isdigit()]
-    per = collections.defaultdict(lambda: [0, 0.0])
+    per = collections.defaultdict(lambda: dict(launches=0, ns=0.0, dram_read=0.0, dram_write=0.0))
     for r in rows:
-        name = r[4].split("(")[0]
-        per[name][0] += 1
-        per[name][1] += num(r[-1])
-    total = sum(v[1] for v in per.values()) or 1.0
-    return {k: dict(launches=v[0], total_ms=v[1] / 1e6, share=v[1] / total) for k, v in per.items()}
+        name, metric, value = r[4].split("(")[0], r[-3], num(r[-1])
+        if metric == "gpu__time_duration.sum":
+            per[name]["launches"] += 1
+            per[name]["ns"] += value
+        elif metric == "dram__bytes_read.sum":
+            per[name]["dram_read"] += value
+        elif metric == "dram__bytes_write.sum":
+            per[name]["dram_write"] += value
+    total = sum(v["ns"] for v in per.values()) or 1.0
+    return {k: dict(launches=v["launches"], total_ms=v["ns"] / 1e6, share=v["ns"] / total,
+                    dram_read_bytes=v["dram_read"], dram_write_bytes=v["dram_write"]) for k, v in per.items()}
 
 
 def ncu_csv(rep, page, extra=()):
@@ -48,7 +56,9 @@ def main():
     if os.path.exists(launches):
         shutil.copy(launches, os.path.join(out_dir, f"{tag}_launches.csv"))
         summary["launch_list"] = launch_shares(launches)
-    rep = os.path.join(src, f"prof_keyed_{tag}.ncu-rep")
+    rep = os.path.join(src, f"prof_subpath_{tag}.ncu-rep")
+    if not os.path.exists(rep):
+        rep = os.path.join(src, f"prof_keyed_{tag}.ncu-rep")
     if os.path.exists(rep):
         raw = ncu_csv(rep, "raw")
         hdr, units, vals = raw[0], raw[1], raw[2]
@@ -99,13 +109,44 @@ def main():
                                     first_instruction=chunk[0]["Source"].strip()))
         summary["full_capture"]["hot_regions_64_instr"] = regions
     json.dump(summary, open(os.path.join(out_dir, f"{tag}_summary.json"), "w"), indent=1)
+    # what bench.py quotes next to its live numbers (roofline.traffic, roofline.ncu)
+    quoted_path = os.path.join(out_dir, "ncu_summary.json")
+    quoted = json.load(open(quoted_path)) if os.path.exists(quoted_path) else {}
+    ours = {k: v for k, v in summary.get("launch_list", {}).items() if "ptb200::" in k and ("Hits" in k or "subPath" in k or "resolve" in k)}
+    if ours and any(v["dram_read_bytes"] or v["dram_write_bytes"] for v in ours.values()):
+        steps = max(1, int(os.environ.get("NCU_STEPS", "2")))  # --steps 1: the value loop and the e2e loop each render once
+        quoted.setdefault("dram_bytes_per_step", {})["1"] = {
+            "bytes": sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in ours.values()) / steps,
+            "per_kernel_per_launch": {k: (v["dram_read_bytes"] + v["dram_write_bytes"]) / max(1, v["launches"]) for k, v in ours.items()},
+            "source": f"profiles/{tag}_launches.csv: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over every "
+                      f"path-tracing launch of one full-size step (640x480 @ 256 spp)"}
+    if "full_capture" in summary:
+        m = summary["full_capture"]["metrics"]
+        quoted["latest_full_capture"] = {
+            "source": f"profiles/{tag}_summary.json (ncu --set full of {m['Kernel Name']['value'].strip()}, BENCH_SPP=16 launch of the bench workload)",
+            "issue_slots_busy_pct": num(m["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"]),
+            "fp64_pipe_active_pct": num(m["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]["value"]),
+            "fma_pipe_pct": num(m["sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]["value"]),
+            "alu_pipe_pct": num(m["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]["value"]),
+            "active_lanes_per_warp_instruction": num(m["smsp__thread_inst_executed_per_inst_executed.ratio"]["value"]),
+            "warps_active_pct_of_peak": num(m["sm__warps_active.avg.pct_of_peak_sustained_active"]["value"]),
+            "registers_per_thread": num(m["launch__registers_per_thread"]["value"])}
+    quoted.pop("dram_bytes_per_launch", None)
+    json.dump(quoted, open(quoted_path, "w"), indent=1)
     with open(os.path.join(out_dir, f"{tag}_summary.md"), "w") as md:
         md.write(f"# ncu summary {tag}\n\n")
         if "launch_list" in summary:
             md.write("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, "
-                     "`python bench.py --steps 2 --warmup 1 --no-cpu-baseline`)\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
+                     "`python bench.py --steps 1 --warmup 0 --no-cpu-baseline`)\n\n| kernel | launches | total ms | share |\n|---|---|---|---|\n")
             for k, v in sorted(summary["launch_list"].items(), key=lambda kv: -kv[1]["share"]):
                 md.write(f"| `{k}` | {v['launches']} | {v['total_ms']:.3f} | {v['share'] * 100:.2f} % |\n")
+            if any(v["dram_read_bytes"] or v["dram_write_bytes"] for v in summary["launch_list"].values()):
+                md.write("\nDRAM traffic of the same launches (`dram__bytes_read.sum`, `dram__bytes_write.sum`):\n\n"
+                         "| kernel | read GB | written GB | per launch MB |\n|---|---|---|---|\n")
+                for k, v in sorted(summary["launch_list"].items(), key=lambda kv: -kv[1]["share"]):
+                    both = v["dram_read_bytes"] + v["dram_write_bytes"]
+                    md.write(f"| `{k}` | {v['dram_read_bytes'] / 1e9:.3f} | {v['dram_write_bytes'] / 1e9:.3f} | "
+                             f"{both / max(1, v['launches']) / 1e6:.1f} |\n")
         if "full_capture" in summary:
             fc = summary["full_capture"]
             md.write("\n## Full capture of the megakernel (`ncu --set full --clock-control none --import-source on`)\n\n")
