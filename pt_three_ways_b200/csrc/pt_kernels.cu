@@ -983,21 +983,17 @@ cudaError_t launchKeyedConfig(const KeyedArgs &args, int numSms, cudaStream_t st
   return cudaGetLastError();
 }
 
-// A megakernel configuration is 10 * launchShape + sweepVariant.
+// A configuration is 10 * launchShape + sweepVariant, + 100 for the three-kernel pipeline.
 //   sweep variants: 0 one-stage FP64; 1 two-stage FP64 (prefilter + exact); 2 FP32 stage 0 + exact;
-//                   3 the same with the packed FP32x2 datapath (FFMA2); 4 = 3 + stage 0 also
-//                   rejects triangles certainly behind the ray (pays off on small scenes);
-//                   5 = 4 and 6 = 3 with the stage-0 decisions kept in sign bits (stage0Reject2)
-//   launch shapes:  0 = 256 threads x 2 CTAs/SM (128 registers); 1 = 384 x 1 (168 registers);
-//                   2 = 256 x 3 (80 registers); 3 = 192 x 4; 4 = 128 x 5 (96 registers); 5 = 192 x 3
-//                   (one big CTA per SM, 640 x 1 / 768 x 1, was measured for the scenes whose tile
-//                   leaves room for only two 256-thread CTAs: no gain on suzanne, -18 % / -29 % on ce
-//                   where every tile hand-over is a CTA-wide barrier; profiles/sweep_*_r1v.jsonl)
-// Default (measured on B200, profiles/r1s): the sign-bit stage 0 WITHOUT the negative-t test
-// (variant 6) everywhere the FP32 filter is usable — 165 vs 156 Msamples/s on Cornell, +5.5 % on
-// suzanne and ce; three CTAs per SM for small scenes, where shading latency rather than the sweep
-// limits the kernel — except for the fp way, whose per-lane engines want the registers of two
-// CTAs per SM (125.6 vs 122.3 Msamples/s, r1t).  PTB200_KEYED_CONFIG overrides it
+//                   3 the same with the packed FP32x2 datapath (FFMA2); 4 = 3 + stage 0 also rejects
+//                   triangles certainly behind the ray; 5 = 4 and 6 = 3 with the stage-0 decisions kept
+//                   in sign bits; 7 = 6 in moment (Pluecker) form.  All of them stay reachable through
+//                   ptb200_intersect (tests); the render kernels are instantiated for 1, 6 and 7 only —
+//                   the others lost every measurement (profiles/README.md).
+//   launch shapes:  0 = 256 threads x 2 CTAs/SM; 2 = 256 x 3; 3 = 192 x 4; 4 = 128 x 5.
+// Default (measured on B200, profiles/r2b..r2d): the pipeline with the moment-form stage 0 wherever the
+// FP32 filter is usable, three CTAs per SM for small scenes (shading latency rather than the sweep
+// limits them), two for scenes whose tile needs the shared memory.  PTB200_KEYED_CONFIG overrides it
 // (tools/sweep_configs.py).
 int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable, int way) {
   static const int forced = [] {
@@ -1018,45 +1014,20 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable, int way) {
 size_t mtHistoryThreadsFor(int numSms) { return static_cast<size_t>(numSms) * 768; }
 
 cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream) {
-  if (args.way == 1) { // the fp way: the default configurations, the unfiltered fallback, sign-bit stage 0
+  if (args.way == 1) { // the fp way: FP64 fallback, sign-bit stage 0 at two / three CTAs per SM
     switch (config) {
     case 1: return launchKeyedConfig<256, 2, 1, 1>(args, numSms, stream);
-    case 3: return launchKeyedConfig<256, 2, 3, 1>(args, numSms, stream);
-    case 4: return launchKeyedConfig<256, 2, 4, 1>(args, numSms, stream);
-    case 24: return launchKeyedConfig<256, 3, 4, 1>(args, numSms, stream);
-    case 5: return launchKeyedConfig<256, 2, 5, 1>(args, numSms, stream);
-    case 25: return launchKeyedConfig<256, 3, 5, 1>(args, numSms, stream);
-    case 45: return launchKeyedConfig<128, 5, 5, 1>(args, numSms, stream);
     case 6: return launchKeyedConfig<256, 2, 6, 1>(args, numSms, stream);
     case 26: return launchKeyedConfig<256, 3, 6, 1>(args, numSms, stream);
     default: return cudaErrorInvalidValue;
     }
   }
+  // The dod estimator with keyed draws in ONE kernel: round 1's form, kept as the A/B reference
+  // of the three-kernel pipeline (pt_split.cu, configurations 100 + ...) that replaced it.
   switch (config) {
-  case 0: return launchKeyedConfig<256, 2, 0>(args, numSms, stream);
   case 1: return launchKeyedConfig<256, 2, 1>(args, numSms, stream);
-  case 2: return launchKeyedConfig<256, 2, 2>(args, numSms, stream);
-  case 3: return launchKeyedConfig<256, 2, 3>(args, numSms, stream);
-  case 11: return launchKeyedConfig<384, 1, 1>(args, numSms, stream);
-  case 13: return launchKeyedConfig<384, 1, 3>(args, numSms, stream);
-  case 21: return launchKeyedConfig<256, 3, 1>(args, numSms, stream);
-  case 23: return launchKeyedConfig<256, 3, 3>(args, numSms, stream);
-  case 4: return launchKeyedConfig<256, 2, 4>(args, numSms, stream);
-  case 24: return launchKeyedConfig<256, 3, 4>(args, numSms, stream);
-  case 34: return launchKeyedConfig<192, 4, 4>(args, numSms, stream);
-  case 33: return launchKeyedConfig<192, 4, 3>(args, numSms, stream);
-  case 43: return launchKeyedConfig<128, 5, 3>(args, numSms, stream);
-  case 54: return launchKeyedConfig<192, 3, 4>(args, numSms, stream);
-  case 44: return launchKeyedConfig<128, 5, 4>(args, numSms, stream);
-  case 5: return launchKeyedConfig<256, 2, 5>(args, numSms, stream);
   case 6: return launchKeyedConfig<256, 2, 6>(args, numSms, stream);
-  case 25: return launchKeyedConfig<256, 3, 5>(args, numSms, stream);
   case 26: return launchKeyedConfig<256, 3, 6>(args, numSms, stream);
-  case 35: return launchKeyedConfig<192, 4, 5>(args, numSms, stream);
-  case 45: return launchKeyedConfig<128, 5, 5>(args, numSms, stream);
-  case 55: return launchKeyedConfig<192, 3, 5>(args, numSms, stream);
-  case 46: return launchKeyedConfig<128, 5, 6>(args, numSms, stream);
-  case 56: return launchKeyedConfig<192, 3, 6>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
 }

@@ -285,6 +285,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
 
   for (;;) {
     // ---- 1. the next sub-path for lanes whose path has ended ----
+    // (Holding one ticket ahead per lane and asking its record into L2 when the ticket is taken was
+    // measured: 193.3 vs 195.0 Msamples/s, profiles/sweep_cornell_r2d.jsonl — the 16 strata of a
+    // record start in adjacent lanes, so one miss already serves sixteen starts.)
     const unsigned needMask = __ballot_sync(kFullMask, needItem);
     if (needMask) {
       const uint32_t want = static_cast<uint32_t>(__popc(needMask));
@@ -297,11 +300,11 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
       } else { // the rest of the old pool, then a fresh one
         uint32_t base = 0;
         if (lane == 0)
-          base = atomicAdd(ticket, static_cast<unsigned int>(kTicketGrab));
+          base = atomicAdd(ticket, kTicketGrab);
         base = __shfl_sync(kFullMask, base, 0);
         item = rank < available ? poolNext + rank : base + (rank - available);
         poolNext = base + (want - available);
-        poolEnd = base + static_cast<uint32_t>(kTicketGrab);
+        poolEnd = base + kTicketGrab;
       }
       if (needItem) {
         needItem = false;
@@ -505,6 +508,9 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
 // =============================================================================================
 // 3. Strata -> samples -> pixels, both sums in the reference's order.
 // =============================================================================================
+// kStrata > 0: the strata count is a compile-time even number (the reference's default 4x4 = 16):
+// the 24-byte terms of a sample are read as 16-byte pairs, the loop is unrolled.
+template <int kStrata>
 __global__ void resolveSamplesKernel(const __grid_constant__ SplitArgs args) {
   const uint32_t own = blockIdx.x * blockDim.x + threadIdx.x;
   if (own >= args.ownPixels)
@@ -512,9 +518,10 @@ __global__ void resolveSamplesKernel(const __grid_constant__ SplitArgs args) {
   const uint32_t px = own % args.width;
   const uint32_t py = static_cast<uint32_t>(args.rowBegin) + (own / args.width) * static_cast<uint32_t>(args.rowStep);
   PtPixelDevice *dst = args.accumulator + (px + static_cast<size_t>(py) * args.width);
-  const uint32_t numSub = args.numSub;
+  const uint32_t numSub = kStrata > 0 ? static_cast<uint32_t>(kStrata) : args.numSub;
   const double invNumSub = 1.0 / static_cast<double>(numSub);
   double r = dst->sum[0], g = dst->sum[1], b = dst->sum[2];
+#pragma unroll 1
   for (uint32_t p = 0; p < args.numPasses; ++p) {
     const size_t sample = static_cast<size_t>(p) * args.ownPixels + own;
     const double *t = args.terms + 3 * sample * numSub;
@@ -523,8 +530,18 @@ __global__ void resolveSamplesKernel(const __grid_constant__ SplitArgs args) {
       colour = mk(t[0], t[1], t[2]);
     } else {
       V3 acc = mk(0, 0, 0);
-      for (uint32_t k = 0; k < numSub; ++k)
-        acc = add(acc, mk(t[3 * k], t[3 * k + 1], t[3 * k + 2]));
+      if (kStrata > 0) {
+        const double2 *pairs = reinterpret_cast<const double2 *>(t); // 3 * kStrata doubles, 16-byte aligned
+#pragma unroll
+        for (int k = 0; k < kStrata; k += 2) { // two terms = three pairs: (x0 y0) (z0 x1) (y1 z1)
+          const double2 a = pairs[3 * (k / 2)], c = pairs[3 * (k / 2) + 1], e = pairs[3 * (k / 2) + 2];
+          acc = add(acc, mk(a.x, a.y, c.x));
+          acc = add(acc, mk(c.y, e.x, e.y));
+        }
+      } else {
+        for (uint32_t k = 0; k < numSub; ++k)
+          acc = add(acc, mk(t[3 * k], t[3 * k + 1], t[3 * k + 2]));
+      }
       colour = scale(acc, invNumSub); // Scene.cpp:178
     }
     r += colour.x;
@@ -600,7 +617,11 @@ static cudaError_t launchSplitShape(const SplitArgs &args, int numSms, cudaStrea
   if (err != cudaSuccess)
     return err;
   const int block = 128;
-  resolveSamplesKernel<<<(args.ownPixels + block - 1) / block, block, 0, stream>>>(args);
+  const unsigned grid = (args.ownPixels + block - 1) / block;
+  if (args.numSub == 16)
+    resolveSamplesKernel<16><<<grid, block, 0, stream>>>(args);
+  else
+    resolveSamplesKernel<0><<<grid, block, 0, stream>>>(args);
   return cudaGetLastError();
 }
 
@@ -615,16 +636,10 @@ cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cud
   case 106: return launchSplitShape<256, 2, 6>(args, numSms, stream);
   case 121: return launchSplitShape<256, 3, 1>(args, numSms, stream);
   case 126: return launchSplitShape<256, 3, 6>(args, numSms, stream);
-  case 136: return launchSplitShape<192, 4, 6>(args, numSms, stream);
-  case 146: return launchSplitShape<128, 5, 6>(args, numSms, stream);
-  case 166: return launchSplitShape<256, 4, 6>(args, numSms, stream);
   case 107: return launchSplitShape<256, 2, 7>(args, numSms, stream);
   case 127: return launchSplitShape<256, 3, 7>(args, numSms, stream);
   case 137: return launchSplitShape<192, 4, 7>(args, numSms, stream);
   case 147: return launchSplitShape<128, 5, 7>(args, numSms, stream);
-  case 167: return launchSplitShape<256, 4, 7>(args, numSms, stream);
-  case 177: return launchSplitShape<224, 4, 7>(args, numSms, stream);
-  case 187: return launchSplitShape<128, 6, 7>(args, numSms, stream);
   default: return cudaErrorInvalidValue;
   }
 }

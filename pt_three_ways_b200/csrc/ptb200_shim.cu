@@ -52,7 +52,11 @@ int fail(int code, const char *format, ...) {
 // 56 B/triangle).
 constexpr uint32_t kResidentTileTriangles = 976; // one resident tile per CTA up to here
 constexpr uint32_t kStreamTileTriangles = 480;   // larger scenes: two buffers of <= this
-constexpr size_t kSampleBufferBytes = size_t(4) << 30;
+// Per-pass sample buffer of the one-kernel forms (24 B per sample).  The sequential stream modes
+// are parallel over passes only, so they want every pass of a call in one launch (up to 4 GiB:
+// 1080p x 86 passes); the fp way is parallel over pixels and batches at 1 GiB.
+constexpr size_t kSequentialSampleBufferBytes = size_t(4) << 30;
+constexpr size_t kSampleBufferBytes = size_t(1) << 30;
 // Keyed pipeline: records + strata terms of one batch of passes (pt_split.cu), ~530 B per sample
 // at 4x4 strata.  Batches of ~2 M samples keep the persistent sub-path kernel's tail below 1 %.
 constexpr size_t kSplitBufferBytes = size_t(1) << 30;
@@ -465,7 +469,7 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
     passesPerBatch = std::max<size_t>(1, kSplitBufferBytes / (pixelsPerPass * perSample));
     passesPerBatch = std::min<size_t>(passesPerBatch, ((uint64_t(1) << 31) - 1) / (numSub * ownPixels));
   } else {
-    passesPerBatch = std::max<size_t>(1, kSampleBufferBytes / (pixelsPerPass * 24));
+    passesPerBatch = std::max<size_t>(1, (sequential ? kSequentialSampleBufferBytes : kSampleBufferBytes) / (pixelsPerPass * 24));
   }
   if (opt.passesPerBatch > 0)
     passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(opt.passesPerBatch));

@@ -237,8 +237,9 @@ def test_progress_callback_runs_on_calling_thread_with_partial_frames(scenes, ca
 
 @pytest.mark.parametrize("scene_name,w,h", [("suzanne", 96, 72), ("cornell", 128, 96), ("ce", 16, 9)])
 def test_every_megakernel_configuration_renders_identically(scene_name, w, h, scenes, tmp_path):
-    """Every megakernel instantiation (sweep variant x launch shape, PTB200_KEYED_CONFIG) must give
-    the same framebuffer and cast count bit for bit."""
+    """Every render-kernel instantiation — the one-kernel form (1, 6, 26) and the three-kernel
+    pipeline (100 + launch shape x sweep variant), PTB200_KEYED_CONFIG — must give the same
+    framebuffer and cast count bit for bit."""
     import os
     import subprocess
     import sys
@@ -250,8 +251,7 @@ def test_every_megakernel_configuration_renders_identically(scene_name, w, h, sc
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
                 root, os.path.join(root, "tests/golden/scenes/%s.ptscene" % scene_name), w, h, w, h)
     outs = []
-    for config in ("1", "0", "2", "3", "4", "13", "24", "43", "5", "6", "25", "26", "35", "46", "56",
-                   "101", "106", "121", "126", "136", "146", "166", "107", "127", "137", "147"):
+    for config in ("1", "6", "26", "101", "106", "121", "126", "107", "127", "137", "147"):
         out = str(tmp_path / f"c{config}.npy")
         res = subprocess.run([sys.executable, "-c", code, out], capture_output=True, text=True,
                              env=dict(os.environ, PTB200_KEYED_CONFIG=config), timeout=300)
