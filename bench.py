@@ -107,6 +107,7 @@ class ClockSampler:
 
     def __init__(self, device_index):
         self.rows = []
+        self.window = []
         self.proc = None
         self.device_index = device_index
 
@@ -122,7 +123,13 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([f.strip() for f in line.split(",")])
+            self.rows.append((time.time(), [f.strip() for f in line.split(",")]))
+
+    def mark(self):
+        """Wall-clock window of the load: the first call opens it, the second closes it.  nvidia-smi
+        itself is started at process start (it needs ~1 s before its first sample, longer than a
+        whole 8-GPU timed region)."""
+        self.window.append(time.time())
 
     def stop(self):
         if self.proc:
@@ -135,7 +142,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lo = self.window[0] if self.window else 0.0
+        hi = self.window[1] if len(self.window) > 1 else float("inf")
+        inside = [row for row in self.rows if lo <= row[0] <= hi + 0.25]
+        for stamp, r in inside or self.rows:  # (a window shorter than one sampling period: whole process)
             try:
                 sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
                 for name, flag in zip(names, r[4:8]):
@@ -275,6 +285,9 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     tag = os.environ.get("MASTER_PORT", str(os.getpid()))
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
     def timed(width, height, spp, steps, warmup, with_e2e=True, sampler=None):
         """Row-partitioned render of one frame at `spp` over all ranks: kernels-only and e2e rates."""
         camera = scene.camera(width, height)
@@ -282,11 +295,11 @@ def run_ours(args):
         options = capi.make_options(rng_mode=capi.RNG_KEYED_PHILOX, device=local_rank,
                                     row_begin=rank, row_step=world)
         samples_total = width * height * spp
+        if sampler:
+            sampler.mark()  # the device is under this load from here (warm-up) to the end of the e2e loop
         for _ in range(warmup):
             ctx.render(camera, params, options)
         barrier()
-        if sampler:
-            sampler.start()
         wall0 = time.perf_counter()
         device_ms, sweep_ms, casts, launches = 0.0, 0.0, 0, 0
         for _ in range(steps):
@@ -299,8 +312,6 @@ def run_ours(args):
             launches += st["kernel_launches"]
         barrier()
         wall = time.perf_counter() - wall0
-        if sampler:
-            sampler.stop()
         device_s = max_over_ranks(device_ms * 1e-3)
         out = {
             "value": samples_total * steps / device_s / 1e6, "device_s": device_s, "wall_s": wall,
@@ -328,9 +339,11 @@ def run_ours(args):
                 out["n_min"], out["n_max"] = int(counts.min()), int(counts.max())
                 out["finite"] = bool(np.isfinite(np.asarray(frame["sum"])).all())
             shared.close()
+        if sampler:
+            sampler.mark()
+            sampler.stop()
         return out
 
-    sampler = ClockSampler(local_rank)
     main = timed(width, height, spp, args.steps, args.warmup, sampler=sampler)
     if rank == 0:
         assert main["n_min"] == spp and main["n_max"] == spp, (main["n_min"], main["n_max"], spp)
