@@ -594,6 +594,63 @@ __device__ __forceinline__ void sweepTileStage0Moment(const float *__restrict__ 
   }
 }
 
+// ---- stage 0 out of the CONSTANT BANK: sweep variant 9, scenes of up to 64 triangles ----------
+// ncu (profiles/r2b) shows the sub-path kernel bound by the L1/shared-memory data pipe (79 % of its
+// peak): a broadcast LDS.128 costs two wavefronts whether it serves one lane or 32, and stage 0
+// issues 19 of them per four triangles — 380 of the ~830 wavefronts of a warp iteration.  The
+// moment-form table of a small scene (76 B/triangle, 3 KB for the Cornell box) fits into the kernel's
+// parameter block, i.e. constant bank 0: with the group loop fully unrolled every table address is an
+// immediate, the compiler loads each float4 with ONE uniform-datapath LDCU.128 into uniform
+// registers and feeds FFMA2/FMUL2 from them directly — no shared-memory wavefronts, no vector
+// registers for triangle data.  Same arithmetic and decisions as sweepTileStage0Moment(), bit for bit.
+constexpr int kConstGroups = 16; // 64 triangles
+struct MomentTable {
+  float4 group[kConstGroups][kMomentFloats];
+};
+// `exact`: the AoS FP64 records of the survivors' test (triExact layout), here in SHARED memory —
+// the gather of 80-byte records was the other big client of the L1 data pipe.
+template <bool kFpWay = false, bool kUnrolled = true>
+__device__ __forceinline__ void sweepConstTable(const MomentTable &table, int groups, const double *exact, V3 o, V3 d,
+                                                Nearest &best) {
+  const MomentRay r = makeMomentRay(o, d);
+  uint32_t rejectedHi = 0xffffffffu, rejectedLo = 0xffffffffu;
+  // kUnrolled: immediate table addresses (LDCU into uniform registers, straight-line code);
+  // otherwise a rolled loop with register-indexed constant loads (LDC.64 into vector registers).
+#pragma unroll(kUnrolled ? kConstGroups : 1)
+  for (int g = 0; g < kConstGroups; ++g) {
+    if (g < groups) { // warp-uniform
+      const float4(&a)[kMomentFloats] = table.group[g];
+      uint32_t r0, r1, r2bits, r3;
+#define PT_LO(k) make_float2(a[k].x, a[k].y)
+#define PT_HI(k) make_float2(a[k].z, a[k].w)
+      stage0RejectMoment(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6), PT_LO(7), PT_LO(8),
+                         PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), PT_LO(13), PT_LO(14), PT_LO(15), PT_LO(16),
+                         PT_LO(17), PT_LO(18), r, r0, r1);
+      stage0RejectMoment(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6), PT_HI(7), PT_HI(8),
+                         PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), PT_HI(13), PT_HI(14), PT_HI(15), PT_HI(16),
+                         PT_HI(17), PT_HI(18), r, r2bits, r3);
+#undef PT_LO
+#undef PT_HI
+      rejectedHi = __funnelshift_l(rejectedLo, rejectedHi, 4);
+      rejectedLo = __funnelshift_l(r0, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r1, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r2bits, rejectedLo, 1);
+      rejectedLo = __funnelshift_l(r3, rejectedLo, 1);
+    }
+  }
+  if (groups <= 0)
+    return;
+  // left-align: triangle k at bit 63 - k; ascending index is the serial loop's tie-break order
+  unsigned long long keep = ~((static_cast<unsigned long long>(rejectedHi) << 32) | rejectedLo) << (64 - 4 * groups);
+  while (keep) {
+    const int i = __clzll(static_cast<long long>(keep));
+    keep &= ~(0x8000000000000000ull >> i);
+    const double2 *record = reinterpret_cast<const double2 *>(exact + 10 * i);
+    const double2 a0 = record[0], a1 = record[1], a2 = record[2], a3 = record[3], a4 = record[4];
+    testTriangle<kFpWay>(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d, i, best);
+  }
+}
+
 // ---- hit epilogues (Scene.cpp:38-48 spheres, :99-112 triangles) ------------------------------
 __device__ __forceinline__ HitInfo finishHit(const DeviceScene &scene,
                                              const double4 *__restrict__ spheres, V3 o, V3 d,

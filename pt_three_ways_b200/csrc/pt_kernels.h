@@ -64,6 +64,8 @@ struct SplitArgs {
   uint8_t *sampleKind;             // [totalSamples] 0: strata terms, 1: colour
   unsigned long long *counters;    // [0] sub-path ticket, [1] casts, [2] records appended
   PtPixelDevice *accumulator;      // full frame
+  MomentTable momentTable;         // sweep variant 9: the stage-0 table of a scene of <= 64 triangles, so that
+                                   //   it lives in constant bank 0 (pt_device.cuh: sweepConstTable)
 };
 
 struct SequentialArgs {
@@ -124,6 +126,7 @@ cudaError_t launchBuildFilter(const BuildFilterArgs &args, cudaStream_t stream);
 cudaError_t launchAuditStage0(const AuditArgs &args, cudaStream_t stream);
 cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cudaStream_t stream);
 size_t splitBytesPerSample(uint32_t numSub);
+bool constTableFits(uint32_t numTriangles, uint32_t numTiles); // sweep variant 9 applies
 cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cudaStream_t stream); // 3 launches
 cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream);
 cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream);

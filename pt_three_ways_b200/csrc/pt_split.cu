@@ -63,10 +63,16 @@ __device__ __forceinline__ uint32_t hitMaterial(const DeviceScene &scene, const 
 // when the scene streams (every thread takes part in the tile hand-over).
 template <int kSweep>
 __device__ __forceinline__ Nearest castRay(const DeviceScene &scene, TileStream &stream, bool resident, bool tracing,
-                                           V3 origin, V3 direction) {
+                                           V3 origin, V3 direction, const MomentTable &table) {
   Nearest best{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim};
   if (tracing)
     sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), origin, direction, best);
+  if (kSweep == 9 || kSweep == 8) { // stage 0 out of the constant bank (8: rolled loop), survivors' records in shared memory
+    if (tracing)
+      sweepConstTable<false, kSweep == 9>(table, static_cast<int>(scene.tileTris / 4),
+                                          reinterpret_cast<const double *>(stream.tile(0)), origin, direction, best);
+    return best;
+  }
   for (uint32_t j = 0; j < scene.numTiles; ++j) {
     const unsigned char *tile = resident ? stream.tile(0) : stream.acquire();
     if (tracing)
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(kBlock) primaryHitsKernel(const __grid_constan
     V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
     if (tracing)
       keyedCameraRay(args.camera, key0, pixel, px, py, origin, direction);
-    const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, origin, direction);
+    const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, origin, direction, args.momentTable);
     casts += tracing ? 1u : 0u;
 
     bool isRecord = false;
@@ -408,7 +414,7 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
     __syncwarp();
 
     // ---- 3. cast ----
-    const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, origin, direction);
+    const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, origin, direction, args.momentTable);
 
     // ---- 4. the hit becomes the next bounce's surface, or the path ends ----
     bool ended = false;
@@ -557,6 +563,10 @@ __global__ void resolveSamplesKernel(const __grid_constant__ SplitArgs args) {
 // =============================================================================================
 // Host-side launchers.
 // =============================================================================================
+bool constTableFits(uint32_t numTriangles, uint32_t numTiles) {
+  return numTiles == 1 && numTriangles <= 4u * kConstGroups;
+}
+
 size_t splitBytesPerSample(uint32_t numSub) {
   return kRecordQuads * sizeof(double2) + 3 * sizeof(double) * static_cast<size_t>(numSub) + 1;
 }
@@ -608,7 +618,7 @@ static cudaError_t launchSubPaths(const SplitArgs &args, int numSms, cudaStream_
 
 template <int kBlock, int kMinBlocks, int kSweep>
 static cudaError_t launchSplitShape(const SplitArgs &args, int numSms, cudaStream_t stream) {
-  cudaError_t err = launchPrimary<256, kSweep>(args, numSms, stream);
+  cudaError_t err = launchPrimary<256, kSweep >= 8 ? 7 : kSweep>(args, numSms, stream);
   if (err != cudaSuccess)
     return err;
   const bool deep = args.maxDepth - 2 > LevelStack<false>::kLevels || args.numMaterials > 0x8000u;
@@ -636,6 +646,12 @@ cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cud
   case 106: return launchSplitShape<256, 2, 6>(args, numSms, stream);
   case 121: return launchSplitShape<256, 3, 1>(args, numSms, stream);
   case 126: return launchSplitShape<256, 3, 6>(args, numSms, stream);
+  case 128: return launchSplitShape<256, 3, 8>(args, numSms, stream);
+  case 148: return launchSplitShape<128, 5, 8>(args, numSms, stream);
+  case 109: return launchSplitShape<256, 2, 9>(args, numSms, stream);
+  case 129: return launchSplitShape<256, 3, 9>(args, numSms, stream);
+  case 149: return launchSplitShape<128, 5, 9>(args, numSms, stream);
+  case 169: return launchSplitShape<256, 4, 9>(args, numSms, stream);
   case 107: return launchSplitShape<256, 2, 7>(args, numSms, stream);
   case 127: return launchSplitShape<256, 3, 7>(args, numSms, stream);
   case 137: return launchSplitShape<192, 4, 7>(args, numSms, stream);

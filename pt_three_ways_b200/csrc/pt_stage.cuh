@@ -24,7 +24,10 @@ constexpr uint32_t kExactBytesPerTriangle = 72;  // 9 doubles
 constexpr uint32_t kFilterBytesPerTriangle = 56; // 14 floats
 constexpr uint32_t kMomentBytesPerTriangle = 76; // 19 floats (sweep variant 7)
 __host__ __device__ inline uint32_t sweepBytesPerTriangle(int sweep) {
-  return sweep == 7 ? kMomentBytesPerTriangle : sweep >= 2 ? kFilterBytesPerTriangle : kExactBytesPerTriangle;
+  return sweep >= 8   ? 80u // variants 8/9 stage the survivors' AoS records (triExact), not a stage-0 tile
+         : sweep == 7 ? kMomentBytesPerTriangle
+         : sweep >= 2 ? kFilterBytesPerTriangle
+                      : kExactBytesPerTriangle;
 }
 
 __host__ __device__ inline uint32_t smemAfterTiles(uint32_t numSpheres, uint32_t tileTris, uint32_t numTiles,
@@ -89,7 +92,8 @@ struct TileStream {
 __device__ __forceinline__ TileStream makeTileStream(unsigned char *smemBase, const DeviceScene &scene,
                                                      int sweep) {
   return TileStream{smemBase,
-                    sweep == 7   ? reinterpret_cast<const unsigned char *>(scene.triMoment)
+                    sweep >= 8   ? reinterpret_cast<const unsigned char *>(scene.triExact)
+                    : sweep == 7 ? reinterpret_cast<const unsigned char *>(scene.triMoment)
                     : sweep >= 2 ? reinterpret_cast<const unsigned char *>(scene.triFilter)
                                : reinterpret_cast<const unsigned char *>(scene.triSweep),
                     scene.tileTris * sweepBytesPerTriangle(sweep), scene.numTiles,

@@ -147,6 +147,8 @@ struct PtContext {
   DeviceBuffer<double> materials;
   DeviceBuffer<float> triFilter;
   DeviceBuffer<float> triMoment;
+  MomentTable momentHost{};    // host copy of triMoment for scenes whose table rides in the kernel parameters
+  bool momentHostValid{false};
   DeviceBuffer<double> triExact;
   double sceneRadius{0};       // >= |p| for every vertex / sphere surface point
   double filterOriginBound{-1}; // origin bound the current triFilter contents were built for
@@ -375,6 +377,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   ctx->sceneRadius = radius;
   ctx->filterUsable = std::isfinite(radius) && radius < 1e6 && longestEdge < 1e6;
   ctx->filterOriginBound = -1;
+  ctx->momentHostValid = false;
 
   PT_CUDA(ctx->triSweep.ensure(sweepDoubles));
   PT_CUDA(ctx->triShade.ensure(shade.size()));
@@ -430,6 +433,14 @@ static int ensureFilter(PtContext *ctx, double originBound, uint64_t *launches) 
   b.originBound = originBound;
   PT_CUDA(launchBuildFilter(b, ctx->stream));
   ctx->filterOriginBound = originBound;
+  ctx->momentHostValid = false;
+  if (constTableFits(ctx->scene.numTriangles, ctx->scene.numTiles)) { // sweep variant 9: table into constant bank 0
+    std::memset(&ctx->momentHost, 0, sizeof ctx->momentHost);
+    PT_CUDA(cudaMemcpyAsync(&ctx->momentHost, ctx->triMoment.ptr, static_cast<size_t>(ctx->scene.tileTris) * 19 * sizeof(float),
+                            cudaMemcpyDeviceToHost, ctx->stream));
+    PT_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->momentHostValid = true;
+  }
   if (launches && ctx->scene.numTiles)
     *launches += 1;
   return PTB200_OK;
@@ -563,6 +574,11 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.sampleKind = ctx->sampleKind.ptr;
       a.counters = ctx->counters.ptr;
       a.accumulator = ctx->accumulator.ptr;
+      if (keyedConfig % 10 >= 8) {
+        if (!ctx->momentHostValid)
+          return fail(PTB200_EINVAL, "sweep variant 9 needs a scene of at most 64 triangles");
+        a.momentTable = ctx->momentHost;
+      }
       PT_CUDA(launchRenderSplit(a, ctx->numSms, keyedConfig, ctx->stream));
       if (events) { // the three kernels of the pipeline are the path-tracing time
         PT_CUDA(cudaEventRecord(e1, ctx->stream));
