@@ -544,6 +544,50 @@ __device__ __forceinline__ MomentRay makeMomentRay(V3 o, V3 d) {
                    static_cast<float>(m.x), static_cast<float>(m.y), static_cast<float>(m.z), one};
 }
 
+// stage0RejectMoment() for FOUR triangles with the two pairs interleaved component by component, so
+// that each float4 of the table is consumed right after it arrives (one 128-bit uniform load instead
+// of two 64-bit ones when the table sits in the constant bank).  Same operations per triangle.
+__device__ __forceinline__ void stage0RejectMoment4(const float4 (&a)[kMomentFloats], const MomentRay &r,
+                                                    uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+#define PT_LO(k) make_float2(a[k].x, a[k].y)
+#define PT_HI(k) make_float2(a[k].z, a[k].w)
+  float2 detL = __fmul2_rn(splat(r.dx), PT_LO(0)), detH = __fmul2_rn(splat(r.dx), PT_HI(0));
+  detL = __ffma2_rn(splat(r.dy), PT_LO(1), detL), detH = __ffma2_rn(splat(r.dy), PT_HI(1), detH);
+  detL = __ffma2_rn(splat(r.dz), PT_LO(2), detL), detH = __ffma2_rn(splat(r.dz), PT_HI(2), detH);
+  float2 xL = __fmul2_rn(splat(r.mx), PT_LO(3)), xH = __fmul2_rn(splat(r.mx), PT_HI(3));
+  xL = __ffma2_rn(splat(r.my), PT_LO(4), xL), xH = __ffma2_rn(splat(r.my), PT_HI(4), xH);
+  xL = __ffma2_rn(splat(r.mz), PT_LO(5), xL), xH = __ffma2_rn(splat(r.mz), PT_HI(5), xH);
+  xL = __ffma2_rn(splat(r.dx), PT_LO(6), xL), xH = __ffma2_rn(splat(r.dx), PT_HI(6), xH);
+  xL = __ffma2_rn(splat(r.dy), PT_LO(7), xL), xH = __ffma2_rn(splat(r.dy), PT_HI(7), xH);
+  xL = __ffma2_rn(splat(r.dz), PT_LO(8), xL), xH = __ffma2_rn(splat(r.dz), PT_HI(8), xH);
+  float2 yL = __fmul2_rn(splat(r.mx), PT_LO(9)), yH = __fmul2_rn(splat(r.mx), PT_HI(9));
+  yL = __ffma2_rn(splat(r.my), PT_LO(10), yL), yH = __ffma2_rn(splat(r.my), PT_HI(10), yH);
+  yL = __ffma2_rn(splat(r.mz), PT_LO(11), yL), yH = __ffma2_rn(splat(r.mz), PT_HI(11), yH);
+  yL = __ffma2_rn(splat(r.dx), PT_LO(12), yL), yH = __ffma2_rn(splat(r.dx), PT_HI(12), yH);
+  yL = __ffma2_rn(splat(r.dy), PT_LO(13), yL), yH = __ffma2_rn(splat(r.dy), PT_HI(13), yH);
+  yL = __ffma2_rn(splat(r.dz), PT_LO(14), yL), yH = __ffma2_rn(splat(r.dz), PT_HI(14), yH);
+  uint32_t s0, s1, s2, s3; // copysign(1, det)
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s0) : "r"(__float_as_uint(detL.x)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s1) : "r"(__float_as_uint(detL.y)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s2) : "r"(__float_as_uint(detH.x)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s3) : "r"(__float_as_uint(detH.y)), "r"(r.one));
+  const float2 sL = make_float2(__uint_as_float(s0), __uint_as_float(s1));
+  const float2 sH = make_float2(__uint_as_float(s2), __uint_as_float(s3));
+  const float2 adetL = make_float2(fabsf(detL.x), fabsf(detL.y)), adetH = make_float2(fabsf(detH.x), fabsf(detH.y));
+  const float2 fL = __fadd2_rn(PT_LO(15), neg2(adetL)), fH = __fadd2_rn(PT_HI(15), neg2(adetH));
+  const float2 aL = __ffma2_rn(xL, sL, PT_LO(16)), aH = __ffma2_rn(xH, sH, PT_HI(16));
+  const float2 bL = __ffma2_rn(yL, sL, PT_LO(17)), bH = __ffma2_rn(yH, sH, PT_HI(17));
+  const float2 boundL = __ffma2_rn(adetL, splat(1.0f + 0x1p-20f), PT_LO(18));
+  const float2 boundH = __ffma2_rn(adetH, splat(1.0f + 0x1p-20f), PT_HI(18));
+  const float2 eL = __ffma2_rn(neg2(__fadd2_rn(xL, yL)), sL, boundL), eH = __ffma2_rn(neg2(__fadd2_rn(xH, yH)), sH, boundH);
+#undef PT_LO
+#undef PT_HI
+  r0 = (__float_as_uint(aL.x) | __float_as_uint(bL.x) | __float_as_uint(eL.x)) & __float_as_uint(fL.x);
+  r1 = (__float_as_uint(aL.y) | __float_as_uint(bL.y) | __float_as_uint(eL.y)) & __float_as_uint(fL.y);
+  r2 = (__float_as_uint(aH.x) | __float_as_uint(bH.x) | __float_as_uint(eH.x)) & __float_as_uint(fH.x);
+  r3 = (__float_as_uint(aH.y) | __float_as_uint(bH.y) | __float_as_uint(eH.y)) & __float_as_uint(fH.y);
+}
+
 // Sweeps a staged tile of moment-form data; same survivor bookkeeping as sweepTileStage0Signs().
 template <bool kFpWay = false>
 __device__ __forceinline__ void sweepTileStage0Moment(const float *__restrict__ filter,
@@ -563,16 +607,7 @@ __device__ __forceinline__ void sweepTileStage0Moment(const float *__restrict__ 
       for (int k = 0; k < kMomentFloats; ++k)
         a[k] = group[k];
       uint32_t r0, r1, r2bits, r3;
-#define PT_LO(k) make_float2(a[k].x, a[k].y)
-#define PT_HI(k) make_float2(a[k].z, a[k].w)
-      stage0RejectMoment(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6), PT_LO(7), PT_LO(8),
-                         PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), PT_LO(13), PT_LO(14), PT_LO(15), PT_LO(16),
-                         PT_LO(17), PT_LO(18), r, r0, r1);
-      stage0RejectMoment(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6), PT_HI(7), PT_HI(8),
-                         PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), PT_HI(13), PT_HI(14), PT_HI(15), PT_HI(16),
-                         PT_HI(17), PT_HI(18), r, r2bits, r3);
-#undef PT_LO
-#undef PT_HI
+      stage0RejectMoment4(a, r, r0, r1, r2bits, r3);
       rejectedHi = __funnelshift_l(rejectedLo, rejectedHi, 4);
       rejectedLo = __funnelshift_l(r0, rejectedLo, 1);
       rejectedLo = __funnelshift_l(r1, rejectedLo, 1);
@@ -591,6 +626,59 @@ __device__ __forceinline__ void sweepTileStage0Moment(const float *__restrict__ 
                     a4 = __ldg(record + 4);
       testTriangle<kFpWay>(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d, firstIndex + i, best);
     }
+  }
+}
+
+// The same sweep for TWO rays of one lane: every group of triangles is loaded once and tested
+// against both (the loads, not the arithmetic, bound the one-ray form: see subPathDualKernel).
+__device__ __forceinline__ void survivorsOfChunk(unsigned long long keep, const double *__restrict__ exact, int chunk,
+                                                 int firstIndex, V3 o, V3 d, Nearest &best) {
+  while (keep) {
+    const int k = __clzll(static_cast<long long>(keep));
+    keep &= ~(0x8000000000000000ull >> k);
+    const int i = chunk + k;
+    const double2 *record = reinterpret_cast<const double2 *>(exact + 10 * static_cast<size_t>(i));
+    const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
+                  a4 = __ldg(record + 4);
+    testTriangle<false>(mk(a0.x, a0.y, a1.x), mk(a1.y, a2.x, a2.y), mk(a3.x, a3.y, a4.x), o, d, firstIndex + i, best);
+  }
+}
+__device__ __forceinline__ void sweepTileStage0Moment2(const float *__restrict__ filter, const double *__restrict__ exact,
+                                                       int count, int firstIndex, V3 o0, V3 d0, bool live0, Nearest &best0,
+                                                       V3 o1, V3 d1, bool live1, Nearest &best1) {
+  const MomentRay ray0 = makeMomentRay(o0, d0), ray1 = makeMomentRay(o1, d1);
+#pragma unroll 1
+  for (int chunk = 0; chunk < count; chunk += 64) {
+    const int chunkEnd = min(count, chunk + 64);
+    uint32_t hi0 = 0xffffffffu, lo0 = 0xffffffffu, hi1 = 0xffffffffu, lo1 = 0xffffffffu;
+    const float4 *group = reinterpret_cast<const float4 *>(filter) + (chunk >> 2) * kMomentFloats;
+    const float4 *const groupEnd = reinterpret_cast<const float4 *>(filter) + (chunkEnd >> 2) * kMomentFloats;
+#pragma unroll 1
+    for (; group != groupEnd; group += kMomentFloats) {
+      float4 a[kMomentFloats];
+#pragma unroll
+      for (int k = 0; k < kMomentFloats; ++k)
+        a[k] = group[k];
+      uint32_t r0, r1, r2, r3;
+      stage0RejectMoment4(a, ray0, r0, r1, r2, r3);
+      hi0 = __funnelshift_l(lo0, hi0, 4);
+      lo0 = __funnelshift_l(r0, lo0, 1);
+      lo0 = __funnelshift_l(r1, lo0, 1);
+      lo0 = __funnelshift_l(r2, lo0, 1);
+      lo0 = __funnelshift_l(r3, lo0, 1);
+      stage0RejectMoment4(a, ray1, r0, r1, r2, r3);
+      hi1 = __funnelshift_l(lo1, hi1, 4);
+      lo1 = __funnelshift_l(r0, lo1, 1);
+      lo1 = __funnelshift_l(r1, lo1, 1);
+      lo1 = __funnelshift_l(r2, lo1, 1);
+      lo1 = __funnelshift_l(r3, lo1, 1);
+    }
+    // left-align: triangle chunk + k at bit 63 - k; the slots past chunkEnd read "rejected"
+    const int shift = 64 - (chunkEnd - chunk);
+    const unsigned long long keep0 = live0 ? ~((static_cast<unsigned long long>(hi0) << 32) | lo0) << shift : 0ull;
+    const unsigned long long keep1 = live1 ? ~((static_cast<unsigned long long>(hi1) << 32) | lo1) << shift : 0ull;
+    survivorsOfChunk(keep0, exact, chunk, firstIndex, o0, d0, best0);
+    survivorsOfChunk(keep1, exact, chunk, firstIndex, o1, d1, best1);
   }
 }
 
@@ -621,16 +709,7 @@ __device__ __forceinline__ void sweepConstTable(const MomentTable &table, int gr
     if (g < groups) { // warp-uniform
       const float4(&a)[kMomentFloats] = table.group[g];
       uint32_t r0, r1, r2bits, r3;
-#define PT_LO(k) make_float2(a[k].x, a[k].y)
-#define PT_HI(k) make_float2(a[k].z, a[k].w)
-      stage0RejectMoment(PT_LO(0), PT_LO(1), PT_LO(2), PT_LO(3), PT_LO(4), PT_LO(5), PT_LO(6), PT_LO(7), PT_LO(8),
-                         PT_LO(9), PT_LO(10), PT_LO(11), PT_LO(12), PT_LO(13), PT_LO(14), PT_LO(15), PT_LO(16),
-                         PT_LO(17), PT_LO(18), r, r0, r1);
-      stage0RejectMoment(PT_HI(0), PT_HI(1), PT_HI(2), PT_HI(3), PT_HI(4), PT_HI(5), PT_HI(6), PT_HI(7), PT_HI(8),
-                         PT_HI(9), PT_HI(10), PT_HI(11), PT_HI(12), PT_HI(13), PT_HI(14), PT_HI(15), PT_HI(16),
-                         PT_HI(17), PT_HI(18), r, r2bits, r3);
-#undef PT_LO
-#undef PT_HI
+      stage0RejectMoment4(a, r, r0, r1, r2bits, r3);
       rejectedHi = __funnelshift_l(rejectedLo, rejectedHi, 4);
       rejectedLo = __funnelshift_l(r0, rejectedLo, 1);
       rejectedLo = __funnelshift_l(r1, rejectedLo, 1);

@@ -1006,7 +1006,15 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable, int way) {
   if (way == 1)
     return filterUsable ? 6 : 1; // the fp way: the megakernel, two CTAs per SM
   const int sweep = filterUsable ? 7 : 1;
-  // the dod estimator with keyed draws: the three-kernel pipeline of pt_split.cu (100 + ...)
+  // the dod estimator with keyed draws: the three-kernel pipeline of pt_split.cu (100 + ...); scenes of
+  // up to 64 triangles keep their stage-0 table in the constant bank (variant 8: 220.6 vs 197.5
+  // Msamples/s on the Cornell box, profiles/README.md r2g)
+  if (filterUsable && numTriangles > 0 && constTableFits(numTriangles, 1))
+    return 128;
+  // scenes whose tile fills the shared memory are bound by its data pipe: two sub-paths per lane share
+  // every group of triangles they load (suzanne 40.0 -> 44.3, ce 3.65 -> 3.91 Msamples/s, r2h)
+  if (filterUsable && !small)
+    return 207;
   return 100 + 10 * (small ? 2 : 0) + sweep;
 }
 

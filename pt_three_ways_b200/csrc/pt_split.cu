@@ -249,11 +249,246 @@ __device__ __forceinline__ bool coneSetup(V3 mirror, double coneTheta, double u,
   return false;
 }
 
-// Per-thread state is kept small on purpose: the ray, six words of path bookkeeping and the level
+// One sub-path's state.  Kept small on purpose: the ray, six words of bookkeeping and the level
 // stack.  The Surface a bounce leaves from never lives in registers across phases: a hit writes it
-// to the thread's shared-memory slot (same 9 x 16-byte layout as a camera-hit record), a new
+// to a shared-memory slot of the thread (same 9 x 16-byte layout as a camera-hit record), a new
 // sub-path points at its record in global memory, and the bounce reads whichever through one
 // generic pointer.
+template <bool kDeep>
+struct SubPath {
+  V3 origin, direction;
+  int depth;              // depth of the ray in flight (>= 1 after the first bounce)
+  uint32_t pixel, key0, subPath;
+  uint32_t termIndex;     // sample * numSub + subPath
+  uint32_t primary;       // the camera hit's material | specular pick << 31
+  LevelStack<kDeep> stack;
+  const double2 *surface; // what the next bounce leaves from (generic: record or slot)
+  bool needItem, finished;
+  __device__ __forceinline__ void init(const double2 *slot) {
+    origin = mk(0, 0, 0);
+    direction = mk(0, 0, 1);
+    depth = 0;
+    pixel = key0 = subPath = termIndex = primary = 0;
+    stack.reset();
+    surface = slot;
+    needItem = true;
+    finished = false;
+  }
+};
+struct TicketPool { // a warp's tickets (warp-uniform)
+  uint32_t next, end;
+};
+
+// ---- 1. the next sub-path for lanes whose path has ended (whole warp) ----
+// (Holding one ticket ahead per lane and asking its record into L2 when the ticket is taken was
+// measured: 193.3 vs 195.0 Msamples/s, profiles/sweep_cornell_r2d.jsonl — the 16 strata of a
+// record start in adjacent lanes, so one miss already serves sixteen starts.)
+template <bool kDeep>
+__device__ __forceinline__ void takeSubPath(const SplitArgs &args, SubPath<kDeep> &path, TicketPool &pool, unsigned lane,
+                                            uint32_t totalItems, unsigned int *ticket) {
+  const unsigned needMask = __ballot_sync(kFullMask, path.needItem);
+  if (!needMask)
+    return;
+  const uint32_t numSub = args.numSub;
+  const uint32_t want = static_cast<uint32_t>(__popc(needMask));
+  const uint32_t rank = static_cast<uint32_t>(__popc(needMask & ((1u << lane) - 1u)));
+  const uint32_t available = pool.end - pool.next;
+  uint32_t item;
+  if (available >= want) {
+    item = pool.next + rank;
+    pool.next += want;
+  } else { // the rest of the old pool, then a fresh one
+    uint32_t base = 0;
+    if (lane == 0)
+      base = atomicAdd(ticket, kTicketGrab);
+    base = __shfl_sync(kFullMask, base, 0);
+    item = rank < available ? pool.next + rank : base + (rank - available);
+    pool.next = base + (want - available);
+    pool.end = base + kTicketGrab;
+  }
+  if (path.needItem) {
+    path.needItem = false;
+    if (item >= totalItems) {
+      path.finished = true;
+    } else {
+      uint32_t recordIndex;
+      if (args.numSubShift >= 0) {
+        recordIndex = item >> args.numSubShift;
+        path.subPath = item & (numSub - 1u);
+      } else {
+        recordIndex = item / numSub;
+        path.subPath = item - recordIndex * numSub;
+      }
+      path.surface = args.records + kRecordQuads * static_cast<size_t>(recordIndex);
+      const double2 q8 = path.surface[8];
+      path.pixel = highWord(q8.x);
+      path.key0 = lowWord(q8.y);
+      path.termIndex = highWord(q8.y) * numSub + path.subPath;
+      path.depth = 0;
+      path.stack.reset();
+    }
+  }
+}
+
+// ---- 2. bounce: one (u, v, p) triple, cone or hemisphere sample (Scene.cpp:157-175) ----
+template <bool kDeep>
+__device__ __forceinline__ void bounceSubPath(const SplitArgs &args, SubPath<kDeep> &path) {
+  const DeviceScene &scene = args.scene;
+  const double2 *surface = path.surface;
+  double ru, rv, rp;
+  KeyedDraws{path.key0}.bounce(path.pixel, path.subPath, static_cast<uint32_t>(path.depth), ru, rv, rp);
+  double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
+  if (path.depth == 0) {
+    // u-major strata (Scene.cpp:155-156); x / n == x * (1/n) exactly when n is a power of two
+    uint32_t stratumU, stratumV;
+    if (args.firstBounceVShift >= 0) {
+      stratumU = path.subPath >> args.firstBounceVShift;
+      stratumV = path.subPath & (static_cast<uint32_t>(args.firstBounceV) - 1u);
+    } else {
+      stratumU = path.subPath / static_cast<uint32_t>(args.firstBounceV);
+      stratumV = path.subPath - stratumU * static_cast<uint32_t>(args.firstBounceV);
+    }
+    const double su = static_cast<double>(stratumU) + ru;
+    const double sv = static_cast<double>(stratumV) + rv;
+    u = args.firstBounceUPow2 ? su * args.invFirstBounceU : ieeeDiv(su, static_cast<double>(args.firstBounceU));
+    v = args.firstBounceVPow2 ? sv * args.invFirstBounceV : ieeeDiv(sv, static_cast<double>(args.firstBounceV));
+  }
+  const double2 q7 = surface[7], q8 = surface[8];
+  const uint32_t surfaceWord = lowWord(q8.x);
+  const uint32_t material = surfaceWord & ~kLazyBasisFlag;
+  const bool specular = rp < q7.y; // p < reflectivity
+  const double2 q1 = surface[1], q2 = surface[2];
+  V3 frameZ = mk(q1.y, q2.x, q2.y); // the surface normal
+  V3 frameX, frameY;
+  double angle = (2 * kPi) * u, radius = 0, zScale = 0;
+  bool direct = false;
+  V3 newDirection = mk(0, 0, 0);
+  // coneSample() / hemisphereSample() (Samples.cpp:6-30) end in the same
+  // normalised(basis.transform(cos(t)*r, sin(t)*r, z)): the few specular lanes only prepare
+  // its inputs, then every lane runs that tail together.
+  if (specular) {
+    const double2 q3 = surface[3], q4 = surface[4];
+    newDirection = reflect(frameZ, mk(q3.x, q3.y, q4.x));
+    direct = coneSetup(newDirection, materialOf(scene, material).coneAngle(), u, v, frameX, frameY, frameZ, angle,
+                       radius, zScale);
+  } else {
+    if (surfaceWord & kLazyBasisFlag) {
+      const Basis basis = basisFromZ(frameZ);
+      frameX = basis.x;
+      frameY = basis.y;
+    } else {
+      const double2 q4 = surface[4], q5 = surface[5], q6 = surface[6];
+      frameX = mk(q4.y, q5.x, q5.y);
+      frameY = mk(q6.x, q6.y, q7.x);
+    }
+    radius = ieeeSqrt(v);
+    zScale = ieeeSqrt(1 - v);
+  }
+  if (!direct) {
+    double sinT, cosT;
+    sinCos(angle, sinT, cosT);
+    newDirection = normalised(transform(Basis{frameX, frameY, frameZ}, mk(cosT * radius, sinT * radius, zScale)));
+  }
+  if (path.depth == 0)
+    path.primary = material | (specular ? 0x80000000u : 0u);
+  else
+    path.stack.set(path.depth, material, specular);
+  const double2 q0 = surface[0];
+  path.origin = mk(q0.x, q0.y, q1.x);
+  path.direction = newDirection;
+  ++path.depth;
+}
+
+// ---- 4. the hit becomes the next bounce's surface (written to `slot`), or the path ends ----
+template <bool kDeep>
+__device__ __forceinline__ void afterCast(const SplitArgs &args, const double4 *spheres, SubPath<kDeep> &path,
+                                          double2 *slot, const Nearest &best, bool tracing) {
+  const DeviceScene &scene = args.scene;
+  const V3 origin = path.origin, direction = path.direction;
+  bool ended = false;
+  V3 incoming = mk(0, 0, 0);
+  if (tracing) {
+    if (best.prim == kNoPrim) {
+      incoming = mk(scene.environment[0], scene.environment[1], scene.environment[2]); // Scene.cpp:132-133
+      ended = true;
+    } else if (path.depth + 1 >= args.maxDepth) {
+      // Deepest level: its sampling loop runs, but every child returns Vec3() (Scene.cpp:128-129).
+      incoming = shadeTerm(materialOf(scene, hitMaterial(scene, best)), true, mk(0, 0, 0));
+      ended = true;
+    } else { // Scene.cpp:135-152 into the slot
+      const V3 position = positionAlong(origin, direction, best.t);
+      V3 normal;
+      uint32_t word;
+      bool inside;
+      double2 q4 = make_double2(direction.z, 0.0), q5 = make_double2(0.0, 0.0), q6 = q5;
+      double basisYz = 0.0;
+      if (best.prim < 0) { // sphere epilogue (Scene.cpp:38-48); its basis is left to the bounce
+        const int i = -best.prim - 1;
+        const double4 s = spheres[i];
+        const V3 outward = normalised(sub(position, mk(s.x, s.y, s.z)));
+        inside = dot(outward, direction) > 0;
+        normal = inside ? neg(outward) : outward;
+        word = __ldg(scene.sphereMaterial + i) | kLazyBasisFlag;
+      } else { // triangle epilogue (Scene.cpp:99-112), normal and bases precomputed at upload
+        const double4 *record = scene.triShade + 4 * static_cast<size_t>(best.prim);
+        const double4 r0 = ldgDouble4(record);
+        const double4 r2 = ldgDouble4(record + 2);
+        inside = best.det < kEpsilon; // backfacing
+        word = static_cast<uint32_t>(r0.w);
+        if (inside) {
+          const double4 r3 = ldgDouble4(record + 3);
+          normal = mk(-r0.x, -r0.y, -r0.z);
+          q4.y = r2.z;
+          q5 = make_double2(r2.w, r3.x);
+          q6 = make_double2(r3.y, r3.z);
+          basisYz = r3.w;
+        } else {
+          const double4 r1 = ldgDouble4(record + 1);
+          normal = mk(r0.x, r0.y, r0.z);
+          q4.y = r1.x;
+          q5 = make_double2(r1.y, r1.z);
+          q6 = make_double2(r1.w, r2.x);
+          basisYz = r2.y;
+        }
+      }
+      HitInfo hit;
+      hit.position = position;
+      hit.normal = normal;
+      hit.inside = inside;
+      const double reflectivity = hitReflectivity(materialOf(scene, word & ~kLazyBasisFlag), hit, direction);
+      slot[0] = make_double2(position.x, position.y);
+      slot[1] = make_double2(position.z, normal.x);
+      slot[2] = make_double2(normal.y, normal.z);
+      slot[3] = make_double2(direction.x, direction.y);
+      slot[4] = q4;
+      slot[5] = q5;
+      slot[6] = q6;
+      slot[7] = make_double2(basisYz, reflectivity);
+      slot[8] = make_double2(packWords(word, 0u), 0.0);
+      path.surface = slot;
+    }
+  }
+  __syncwarp();
+  if (ended) {
+    // unwind levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum), then the camera
+    // hit's own term for this stratum
+#pragma unroll 1
+    for (int level = path.depth - 1; level >= 1; --level) {
+      uint32_t material;
+      bool specular;
+      path.stack.get(level, material, specular);
+      incoming = shadeTerm(materialOf(scene, material), specular, incoming);
+    }
+    const V3 term = shadeTerm(materialOf(scene, path.primary & 0x7fffffffu), (path.primary >> 31) != 0, incoming);
+    double *out = args.terms + 3 * static_cast<size_t>(path.termIndex);
+    out[0] = term.x;
+    out[1] = term.y;
+    out[2] = term.z;
+    path.needItem = true;
+  }
+  __syncwarp();
+}
+
 template <int kBlock, int kMinBlocks, int kSweep, bool kDeep>
 __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid_constant__ SplitArgs args) {
   extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -272,233 +507,119 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks) subPathKernel(const __grid
                         kRecordQuads * threadIdx.x;
 
   const unsigned lane = threadIdx.x & 31u;
-  const uint32_t numSub = args.numSub;
-  const uint32_t totalItems = static_cast<uint32_t>(args.counters[2]) * numSub; // records x strata, < 2^31
+  const uint32_t totalItems = static_cast<uint32_t>(args.counters[2]) * args.numSub; // records x strata, < 2^31
   unsigned int *const ticket = reinterpret_cast<unsigned int *>(args.counters);
-
-  // ---- per-lane path state ----
-  V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
-  int depth = 0;              // depth of the ray in flight (>= 1 after the first bounce)
-  uint32_t pixel = 0, key0 = 0, subPath = 0;
-  uint32_t termIndex = 0;     // sample * numSub + subPath
-  uint32_t primary = 0;       // the camera hit's material | specular pick << 31
-  uint32_t casts = 0;         // per lane and launch: far below 2^32
-  LevelStack<kDeep> stack;
-  stack.reset();
-  const double2 *surface = slot; // what the next bounce leaves from (generic: record or slot)
-  bool needItem = true, finished = false;
-  uint32_t poolNext = 0, poolEnd = 0; // this warp's tickets (warp-uniform)
+  SubPath<kDeep> path;
+  path.init(slot);
+  TicketPool pool{0, 0};
+  uint32_t casts = 0; // per lane and launch: far below 2^32
 
   for (;;) {
-    // ---- 1. the next sub-path for lanes whose path has ended ----
-    // (Holding one ticket ahead per lane and asking its record into L2 when the ticket is taken was
-    // measured: 193.3 vs 195.0 Msamples/s, profiles/sweep_cornell_r2d.jsonl — the 16 strata of a
-    // record start in adjacent lanes, so one miss already serves sixteen starts.)
-    const unsigned needMask = __ballot_sync(kFullMask, needItem);
-    if (needMask) {
-      const uint32_t want = static_cast<uint32_t>(__popc(needMask));
-      const uint32_t rank = static_cast<uint32_t>(__popc(needMask & ((1u << lane) - 1u)));
-      const uint32_t available = poolEnd - poolNext;
-      uint32_t item;
-      if (available >= want) {
-        item = poolNext + rank;
-        poolNext += want;
-      } else { // the rest of the old pool, then a fresh one
-        uint32_t base = 0;
-        if (lane == 0)
-          base = atomicAdd(ticket, kTicketGrab);
-        base = __shfl_sync(kFullMask, base, 0);
-        item = rank < available ? poolNext + rank : base + (rank - available);
-        poolNext = base + (want - available);
-        poolEnd = base + kTicketGrab;
-      }
-      if (needItem) {
-        needItem = false;
-        if (item >= totalItems) {
-          finished = true;
-        } else {
-          uint32_t recordIndex;
-          if (args.numSubShift >= 0) {
-            recordIndex = item >> args.numSubShift;
-            subPath = item & (numSub - 1u);
-          } else {
-            recordIndex = item / numSub;
-            subPath = item - recordIndex * numSub;
-          }
-          surface = args.records + kRecordQuads * static_cast<size_t>(recordIndex);
-          const double2 q8 = surface[8];
-          pixel = highWord(q8.x);
-          key0 = lowWord(q8.y);
-          termIndex = highWord(q8.y) * numSub + subPath;
-          depth = 0;
-          stack.reset();
-        }
-      }
-    }
+    takeSubPath(args, path, pool, lane, totalItems, ticket);
     __syncwarp();
     if (resident) {
-      if (__all_sync(kFullMask, finished))
+      if (__all_sync(kFullMask, path.finished))
         break;
     } else {
-      if (__syncthreads_and(finished))
+      if (__syncthreads_and(path.finished))
         break;
     }
-    const bool tracing = !finished;
-
-    // ---- 2. bounce: one (u, v, p) triple, cone or hemisphere sample (Scene.cpp:157-175) ----
+    const bool tracing = !path.finished;
     if (tracing) {
-      double ru, rv, rp;
-      KeyedDraws{key0}.bounce(pixel, subPath, static_cast<uint32_t>(depth), ru, rv, rp);
-      double u = ru, v = rv; // (0 + r) / 1 exactly, below the first bounce
-      if (depth == 0) {
-        // u-major strata (Scene.cpp:155-156); x / n == x * (1/n) exactly when n is a power of two
-        uint32_t stratumU, stratumV;
-        if (args.firstBounceVShift >= 0) {
-          stratumU = subPath >> args.firstBounceVShift;
-          stratumV = subPath & (static_cast<uint32_t>(args.firstBounceV) - 1u);
-        } else {
-          stratumU = subPath / static_cast<uint32_t>(args.firstBounceV);
-          stratumV = subPath - stratumU * static_cast<uint32_t>(args.firstBounceV);
-        }
-        const double su = static_cast<double>(stratumU) + ru;
-        const double sv = static_cast<double>(stratumV) + rv;
-        u = args.firstBounceUPow2 ? su * args.invFirstBounceU : ieeeDiv(su, static_cast<double>(args.firstBounceU));
-        v = args.firstBounceVPow2 ? sv * args.invFirstBounceV : ieeeDiv(sv, static_cast<double>(args.firstBounceV));
-      }
-      const double2 q7 = surface[7], q8 = surface[8];
-      const uint32_t surfaceWord = lowWord(q8.x);
-      const uint32_t material = surfaceWord & ~kLazyBasisFlag;
-      const bool specular = rp < q7.y; // p < reflectivity
-      const double2 q1 = surface[1], q2 = surface[2];
-      V3 frameZ = mk(q1.y, q2.x, q2.y); // the surface normal
-      V3 frameX, frameY;
-      double angle = (2 * kPi) * u, radius = 0, zScale = 0;
-      bool direct = false;
-      V3 newDirection = mk(0, 0, 0);
-      // coneSample() / hemisphereSample() (Samples.cpp:6-30) end in the same
-      // normalised(basis.transform(cos(t)*r, sin(t)*r, z)): the few specular lanes only prepare
-      // its inputs, then every lane runs that tail together.
-      if (specular) {
-        const double2 q3 = surface[3], q4 = surface[4];
-        newDirection = reflect(frameZ, mk(q3.x, q3.y, q4.x));
-        direct = coneSetup(newDirection, materialOf(scene, material).coneAngle(), u, v, frameX, frameY, frameZ,
-                           angle, radius, zScale);
-      } else {
-        if (surfaceWord & kLazyBasisFlag) {
-          const Basis basis = basisFromZ(frameZ);
-          frameX = basis.x;
-          frameY = basis.y;
-        } else {
-          const double2 q4 = surface[4], q5 = surface[5], q6 = surface[6];
-          frameX = mk(q4.y, q5.x, q5.y);
-          frameY = mk(q6.x, q6.y, q7.x);
-        }
-        radius = ieeeSqrt(v);
-        zScale = ieeeSqrt(1 - v);
-      }
-      if (!direct) {
-        double sinT, cosT;
-        sinCos(angle, sinT, cosT);
-        newDirection = normalised(transform(Basis{frameX, frameY, frameZ}, mk(cosT * radius, sinT * radius, zScale)));
-      }
-      if (depth == 0)
-        primary = material | (specular ? 0x80000000u : 0u);
-      else
-        stack.set(depth, material, specular);
-      const double2 q0 = surface[0];
-      origin = mk(q0.x, q0.y, q1.x);
-      direction = newDirection;
-      ++depth;
+      bounceSubPath(args, path);
+      ++casts;
+    }
+    __syncwarp();
+    const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, path.origin, path.direction, args.momentTable);
+    afterCast(args, stream.spheres(), path, slot, best, tracing);
+  }
+
+  if (!resident)
+    stream.drain();
+  unsigned long long warpCasts = casts;
+#pragma unroll 1
+  for (int offset = 16; offset > 0; offset >>= 1)
+    warpCasts += __shfl_down_sync(kFullMask, warpCasts, offset);
+  if (lane == 0 && warpCasts)
+    atomicAdd(args.counters + 1, warpCasts);
+}
+
+// ---- two sub-paths per lane -------------------------------------------------------------------
+// Scenes whose stage-0 tile sits in shared memory are bound by the shared-memory data pipe, not by
+// issue slots: a broadcast LDS.128 costs two wavefronts, stage 0 needs 19 of them per four
+// triangles, i.e. 38 pipe cycles against ~20 issue cycles per SM (suzanne: 9 200 wavefronts per warp
+// iteration).  Here every lane carries TWO sub-paths and sweeps both rays against each group of
+// triangles it loads, which halves the wavefronts per ray; one CTA of kBlock threads per SM so that
+// the tile is staged once.
+template <int kBlock, bool kDeep>
+__global__ void __launch_bounds__(kBlock, 1) subPathDualKernel(const __grid_constant__ SplitArgs args) {
+  constexpr int kSweep = 7;
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  const DeviceScene &scene = args.scene;
+  TileStream stream = makeTileStream(smemRaw, scene, kSweep);
+  stream.start();
+#pragma unroll 1
+  for (uint32_t i = threadIdx.x; i < scene.numSpheres; i += kBlock)
+    stream.spheres()[i] = scene.spheres[i];
+  __syncthreads();
+  const bool resident = scene.numTiles <= 1;
+  if (resident && scene.numTiles == 1)
+    stream.acquire();
+  double2 *const slot0 = reinterpret_cast<double2 *>(smemRaw + smemAfterTiles(scene.numSpheres, scene.tileTris,
+                                                                              scene.numTiles, kSweep)) +
+                         2 * kRecordQuads * threadIdx.x;
+  double2 *const slot1 = slot0 + kRecordQuads;
+
+  const unsigned lane = threadIdx.x & 31u;
+  const uint32_t totalItems = static_cast<uint32_t>(args.counters[2]) * args.numSub;
+  unsigned int *const ticket = reinterpret_cast<unsigned int *>(args.counters);
+  SubPath<kDeep> path0, path1;
+  path0.init(slot0);
+  path1.init(slot1);
+  TicketPool pool{0, 0};
+  uint32_t casts = 0;
+
+  for (;;) {
+    takeSubPath(args, path0, pool, lane, totalItems, ticket);
+    takeSubPath(args, path1, pool, lane, totalItems, ticket);
+    __syncwarp();
+    const bool done = path0.finished && path1.finished;
+    if (resident) {
+      if (__all_sync(kFullMask, done))
+        break;
+    } else {
+      if (__syncthreads_and(done))
+        break;
+    }
+    const bool tracing0 = !path0.finished, tracing1 = !path1.finished;
+    if (tracing0) {
+      bounceSubPath(args, path0);
+      ++casts;
+    }
+    __syncwarp();
+    if (tracing1) {
+      bounceSubPath(args, path1);
       ++casts;
     }
     __syncwarp();
 
-    // ---- 3. cast ----
-    const Nearest best = castRay<kSweep>(scene, stream, resident, tracing, origin, direction, args.momentTable);
-
-    // ---- 4. the hit becomes the next bounce's surface, or the path ends ----
-    bool ended = false;
-    V3 incoming = mk(0, 0, 0);
-    if (tracing) {
-      if (best.prim == kNoPrim) {
-        incoming = mk(scene.environment[0], scene.environment[1], scene.environment[2]); // Scene.cpp:132-133
-        ended = true;
-      } else if (depth + 1 >= args.maxDepth) {
-        // Deepest level: its sampling loop runs, but every child returns Vec3() (Scene.cpp:128-129).
-        incoming = shadeTerm(materialOf(scene, hitMaterial(scene, best)), true, mk(0, 0, 0));
-        ended = true;
-      } else { // Scene.cpp:135-152 into the slot
-        const V3 position = positionAlong(origin, direction, best.t);
-        V3 normal;
-        uint32_t word;
-        bool inside;
-        double2 q4 = make_double2(direction.z, 0.0), q5 = make_double2(0.0, 0.0), q6 = q5;
-        double basisYz = 0.0;
-        if (best.prim < 0) { // sphere epilogue (Scene.cpp:38-48); its basis is left to the bounce
-          const int i = -best.prim - 1;
-          const double4 s = stream.spheres()[i];
-          const V3 outward = normalised(sub(position, mk(s.x, s.y, s.z)));
-          inside = dot(outward, direction) > 0;
-          normal = inside ? neg(outward) : outward;
-          word = __ldg(scene.sphereMaterial + i) | kLazyBasisFlag;
-        } else { // triangle epilogue (Scene.cpp:99-112), normal and bases precomputed at upload
-          const double4 *record = scene.triShade + 4 * static_cast<size_t>(best.prim);
-          const double4 r0 = ldgDouble4(record);
-          const double4 r2 = ldgDouble4(record + 2);
-          inside = best.det < kEpsilon; // backfacing
-          word = static_cast<uint32_t>(r0.w);
-          if (inside) {
-            const double4 r3 = ldgDouble4(record + 3);
-            normal = mk(-r0.x, -r0.y, -r0.z);
-            q4.y = r2.z;
-            q5 = make_double2(r2.w, r3.x);
-            q6 = make_double2(r3.y, r3.z);
-            basisYz = r3.w;
-          } else {
-            const double4 r1 = ldgDouble4(record + 1);
-            normal = mk(r0.x, r0.y, r0.z);
-            q4.y = r1.x;
-            q5 = make_double2(r1.y, r1.z);
-            q6 = make_double2(r1.w, r2.x);
-            basisYz = r2.y;
-          }
-        }
-        HitInfo hit;
-        hit.position = position;
-        hit.normal = normal;
-        hit.inside = inside;
-        const double reflectivity = hitReflectivity(materialOf(scene, word & ~kLazyBasisFlag), hit, direction);
-        slot[0] = make_double2(position.x, position.y);
-        slot[1] = make_double2(position.z, normal.x);
-        slot[2] = make_double2(normal.y, normal.z);
-        slot[3] = make_double2(direction.x, direction.y);
-        slot[4] = q4;
-        slot[5] = q5;
-        slot[6] = q6;
-        slot[7] = make_double2(basisYz, reflectivity);
-        slot[8] = make_double2(packWords(word, 0u), 0.0);
-        surface = slot;
-      }
+    // Scene::intersect for both rays: spheres first, then every tile (Scene.cpp:115-122)
+    Nearest best0{__longlong_as_double(0x7ff0000000000000ll), 0.0, kNoPrim}, best1 = best0;
+    if (tracing0)
+      sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), path0.origin, path0.direction, best0);
+    if (tracing1)
+      sweepSpheres(stream.spheres(), static_cast<int>(scene.numSpheres), path1.origin, path1.direction, best1);
+    for (uint32_t j = 0; j < scene.numTiles; ++j) {
+      const unsigned char *tile = resident ? stream.tile(0) : stream.acquire();
+      const int first = static_cast<int>(j * scene.tileTris);
+      sweepTileStage0Moment2(reinterpret_cast<const float *>(tile), scene.triExact + static_cast<size_t>(first) * 10,
+                             static_cast<int>(scene.tileTris), first, path0.origin, path0.direction, tracing0, best0,
+                             path1.origin, path1.direction, tracing1, best1);
+      if (!resident)
+        stream.release();
     }
-    __syncwarp();
-    if (ended) {
-      // unwind levels depth-1 .. 1 (Scene.cpp:168,172-174 with a 1x1 stratum), then the camera
-      // hit's own term for this stratum
-#pragma unroll 1
-      for (int level = depth - 1; level >= 1; --level) {
-        uint32_t material;
-        bool specular;
-        stack.get(level, material, specular);
-        incoming = shadeTerm(materialOf(scene, material), specular, incoming);
-      }
-      const V3 term = shadeTerm(materialOf(scene, primary & 0x7fffffffu), (primary >> 31) != 0, incoming);
-      double *out = args.terms + 3 * static_cast<size_t>(termIndex);
-      out[0] = term.x;
-      out[1] = term.y;
-      out[2] = term.z;
-      needItem = true;
-    }
-    __syncwarp();
+    afterCast(args, stream.spheres(), path0, slot0, best0, tracing0);
+    afterCast(args, stream.spheres(), path1, slot1, best1, tracing1);
   }
 
   if (!resident)
@@ -616,6 +737,47 @@ static cudaError_t launchSubPaths(const SplitArgs &args, int numSms, cudaStream_
   return cudaGetLastError();
 }
 
+template <int kBlock, bool kDeep>
+static cudaError_t launchSubPathsDual(const SplitArgs &args, int numSms, cudaStream_t stream) {
+  auto kernel = subPathDualKernel<kBlock, kDeep>;
+  const size_t smemBytes = smemAfterTiles(args.scene.numSpheres, args.scene.tileTris, args.scene.numTiles, 7) +
+                           static_cast<size_t>(kBlock) * 2 * kRecordQuads * sizeof(double2); // two Surface slots per thread
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smemBytes));
+  if (err != cudaSuccess)
+    return err;
+  int perSm = 0;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, kBlock, smemBytes);
+  if (err != cudaSuccess)
+    return err;
+  if (perSm < 1)
+    return cudaErrorInvalidConfiguration;
+  const unsigned long long wanted = (static_cast<unsigned long long>(args.totalSamples) * args.numSub + 2 * kBlock - 1) / (2 * kBlock);
+  unsigned long long grid = static_cast<unsigned long long>(numSms) * perSm;
+  if (wanted < grid)
+    grid = wanted ? wanted : 1;
+  kernel<<<static_cast<unsigned>(grid), kBlock, smemBytes, stream>>>(args);
+  return cudaGetLastError();
+}
+
+// The pipeline with two sub-paths per lane in the middle kernel (configurations 200 + 10 * shape + 7).
+template <int kBlock>
+static cudaError_t launchSplitDual(const SplitArgs &args, int numSms, cudaStream_t stream) {
+  cudaError_t err = launchPrimary<256, 7>(args, numSms, stream);
+  if (err != cudaSuccess)
+    return err;
+  const bool deep = args.maxDepth - 2 > LevelStack<false>::kLevels || args.numMaterials > 0x8000u;
+  err = deep ? launchSubPathsDual<kBlock, true>(args, numSms, stream) : launchSubPathsDual<kBlock, false>(args, numSms, stream);
+  if (err != cudaSuccess)
+    return err;
+  const int block = 128;
+  const unsigned grid = (args.ownPixels + block - 1) / block;
+  if (args.numSub == 16)
+    resolveSamplesKernel<16><<<grid, block, 0, stream>>>(args);
+  else
+    resolveSamplesKernel<0><<<grid, block, 0, stream>>>(args);
+  return cudaGetLastError();
+}
+
 template <int kBlock, int kMinBlocks, int kSweep>
 static cudaError_t launchSplitShape(const SplitArgs &args, int numSms, cudaStream_t stream) {
   cudaError_t err = launchPrimary<256, kSweep >= 8 ? 7 : kSweep>(args, numSms, stream);
@@ -642,11 +804,16 @@ static cudaError_t launchSplitShape(const SplitArgs &args, int numSms, cudaStrea
 // 6 = 256 x 4.
 cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cudaStream_t stream) {
   switch (config) {
+  case 207: return launchSplitDual<384>(args, numSms, stream);
+  case 217: return launchSplitDual<512>(args, numSms, stream);
+  case 227: return launchSplitDual<256>(args, numSms, stream);
   case 101: return launchSplitShape<256, 2, 1>(args, numSms, stream);
   case 106: return launchSplitShape<256, 2, 6>(args, numSms, stream);
   case 121: return launchSplitShape<256, 3, 1>(args, numSms, stream);
   case 126: return launchSplitShape<256, 3, 6>(args, numSms, stream);
   case 128: return launchSplitShape<256, 3, 8>(args, numSms, stream);
+  case 168: return launchSplitShape<256, 4, 8>(args, numSms, stream);
+  case 188: return launchSplitShape<192, 5, 8>(args, numSms, stream);
   case 148: return launchSplitShape<128, 5, 8>(args, numSms, stream);
   case 109: return launchSplitShape<256, 2, 9>(args, numSms, stream);
   case 129: return launchSplitShape<256, 3, 9>(args, numSms, stream);

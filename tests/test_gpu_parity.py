@@ -251,7 +251,8 @@ def test_every_megakernel_configuration_renders_identically(scene_name, w, h, sc
             "np.save(sys.argv[1], px['sum']); print(st['casts'])\n") % (
                 root, os.path.join(root, "tests/golden/scenes/%s.ptscene" % scene_name), w, h, w, h)
     outs = []
-    configs = ["1", "6", "26", "101", "106", "121", "126", "107", "127", "137", "147"]
+    configs = ["1", "6", "26", "101", "106", "121", "126", "107", "127", "137", "147",
+               "207", "217", "227"]  # 2xx: two sub-paths per lane
     if scene_name == "cornell":  # stage 0 out of the constant bank: scenes of up to 64 triangles
         configs += ["109", "129", "149", "169", "128", "148"]
     for config in configs:
