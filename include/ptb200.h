@@ -200,6 +200,10 @@ int ptb200_context_download(PtContext *ctx, PtPixel *out);
  * TFLOP/s (2 flops per FMA) and the kernel time. */
 int ptb200_measure_fp64_peak(int32_t device, double *tflops, double *milliseconds);
 
+/* The same for the packed FP32 FMA (FFMA2, 4 flops each): the roof of the FP32 stage-0 sweep that
+ * binds the triangle-heavy scenes. */
+int ptb200_measure_fp32_peak(int32_t device, double *tflops, double *milliseconds);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,7 +24,7 @@ EXPORTS = [
     "ptb200_last_error", "ptb200_device_count", "ptb200_render", "ptb200_render_multi",
     "ptb200_intersect", "ptb200_context_create", "ptb200_context_destroy",
     "ptb200_context_upload_scene", "ptb200_context_render", "ptb200_context_download",
-    "ptb200_measure_fp64_peak",
+    "ptb200_measure_fp64_peak", "ptb200_measure_fp32_peak",
 ]
 
 
@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
         _lib.ptb200_intersect.argtypes = [C.POINTER(PtScene), C.c_int32, C.c_int32, C.c_double,
                                           C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.ptb200_measure_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double),
+                                                  C.POINTER(C.c_double)]
+        _lib.ptb200_measure_fp32_peak.argtypes = [C.c_int32, C.POINTER(C.c_double),
                                                   C.POINTER(C.c_double)]
         _lib.ptb200_device_count.argtypes = [C.POINTER(C.c_int32)]
     return _lib
@@ -274,4 +276,10 @@ class Context:
 def measure_fp64_peak(device=0):
     t, ms = C.c_double(0), C.c_double(0)
     _check(lib().ptb200_measure_fp64_peak(device, C.byref(t), C.byref(ms)))
+    return t.value, ms.value
+
+
+def measure_fp32_peak(device=0):
+    t, ms = C.c_double(0), C.c_double(0)
+    _check(lib().ptb200_measure_fp32_peak(device, C.byref(t), C.byref(ms)))
     return t.value, ms.value

@@ -705,8 +705,8 @@ __device__ __forceinline__ void sweepConstTable(const MomentTable &table, int gr
   // kUnrolled: immediate table addresses (LDCU into uniform registers, straight-line code);
   // otherwise a rolled loop with register-indexed constant loads (LDC.64 into vector registers).
 #pragma unroll(kUnrolled ? kConstGroups : 1)
-  for (int g = 0; g < kConstGroups; ++g) {
-    if (g < groups) { // warp-uniform
+  for (int g = 0; g < (kUnrolled ? kConstGroups : groups); ++g) {
+    if (!kUnrolled || g < groups) { // warp-uniform
       const float4(&a)[kMomentFloats] = table.group[g];
       uint32_t r0, r1, r2bits, r3;
       stage0RejectMoment4(a, r, r0, r1, r2bits, r3);

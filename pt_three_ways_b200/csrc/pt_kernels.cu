@@ -952,6 +952,22 @@ __global__ void fp64PeakKernel(double *sink, int iterations) {
     sink[0] = total;
 }
 
+// Packed-FP32 throughput probe (FFMA2, the instruction of the stage-0 sweep): 8 independent chains.
+__global__ void fp32PeakKernel(float *sink, int iterations) {
+  float2 a0 = make_float2(threadIdx.x * 1e-6f, 1.f), a1 = a0, a2 = a0, a3 = a0, a4 = a0, a5 = a0, a6 = a0, a7 = a0;
+  const float2 m = make_float2(1.0000001f, 0.9999999f), c = make_float2(1e-7f, -1e-7f);
+  for (int i = 0; i < iterations; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      a0 = __ffma2_rn(a0, m, c); a1 = __ffma2_rn(a1, m, c); a2 = __ffma2_rn(a2, m, c); a3 = __ffma2_rn(a3, m, c);
+      a4 = __ffma2_rn(a4, m, c); a5 = __ffma2_rn(a5, m, c); a6 = __ffma2_rn(a6, m, c); a7 = __ffma2_rn(a7, m, c);
+    }
+  }
+  const float total = (a0.x + a1.y) + (a2.x + a3.y) + (a4.x + a5.y) + (a6.x + a7.y);
+  if (total == 12345.678f)
+    sink[0] = total;
+}
+
 // =============================================================================================
 // Host-side launchers (called from ptb200_shim.cu).
 // =============================================================================================
@@ -1080,6 +1096,11 @@ cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream) {
   const int block = 128;
   const int grid = static_cast<int>((args.numRays + block - 1) / block);
   intersectKernel<<<grid, block, smemBytes, stream>>>(args);
+  return cudaGetLastError();
+}
+
+cudaError_t launchFp32Peak(float *sink, int iterations, int blocks, int threads, cudaStream_t stream) {
+  fp32PeakKernel<<<blocks, threads, 0, stream>>>(sink, iterations);
   return cudaGetLastError();
 }
 

@@ -133,5 +133,6 @@ cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream);
 cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream);
 cudaError_t launchFp64Peak(double *sink, int iterations, int blocks, int threads,
                            cudaStream_t stream);
+cudaError_t launchFp32Peak(float *sink, int iterations, int blocks, int threads, cudaStream_t stream);
 
 } // namespace ptb200

@@ -959,6 +959,46 @@ int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double
   return rc;
 }
 
+int ptb200_measure_fp32_peak(int32_t device, double *tflops, double *milliseconds) {
+  if (!tflops)
+    return fail(PTB200_EINVAL, "null argument");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return fail(PTB200_ECUDA, "no CUDA device available");
+  }
+  PT_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop{};
+  PT_CUDA(cudaGetDeviceProperties(&prop, device));
+  DeviceBuffer<float> sink;
+  PT_CUDA(sink.ensure(1));
+  const int threads = 512, blocks = prop.multiProcessorCount * 4, iterations = 4096;
+  EventList owned;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  PT_CUDA(owned.make(&e0));
+  PT_CUDA(owned.make(&e1));
+  double best = 0, bestMs = 0;
+  for (int rep = 0; rep < 5; ++rep) { // first repetitions warm up
+    PT_CUDA(cudaEventRecord(e0, nullptr));
+    PT_CUDA(launchFp32Peak(sink.ptr, iterations, blocks, threads, nullptr));
+    PT_CUDA(cudaEventRecord(e1, nullptr));
+    PT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    PT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    // one FFMA2 = two lanes x (multiply + add) = 4 flop; 8 chains x 16 per iteration
+    const double flops = 4.0 * 8 * 16 * static_cast<double>(iterations) * threads * blocks;
+    const double rate = flops / (ms * 1e-3) / 1e12;
+    if (rate > best) {
+      best = rate;
+      bestMs = ms;
+    }
+  }
+  *tflops = best;
+  if (milliseconds)
+    *milliseconds = bestMs;
+  return PTB200_OK;
+}
+
 int ptb200_measure_fp64_peak(int32_t device, double *tflops, double *milliseconds) {
   if (!tflops)
     return fail(PTB200_EINVAL, "null argument");

@@ -48,15 +48,16 @@ def ncu_csv(rep, page, extra=()):
 
 def main():
     tag = sys.argv[1]
+    label = sys.argv[2] if len(sys.argv) > 2 else ""  # e.g. "suzanne": gpurun_out/prof_suzanne_<tag>.ncu-rep only
     out_dir = os.path.join(ROOT, "profiles")
     src = os.path.join(ROOT, "gpurun_out")
     os.makedirs(out_dir, exist_ok=True)
     summary = {"tag": tag}
     launches = os.path.join(src, f"launches_{tag}.csv")
-    if os.path.exists(launches):
+    if os.path.exists(launches) and not label:
         shutil.copy(launches, os.path.join(out_dir, f"{tag}_launches.csv"))
         summary["launch_list"] = launch_shares(launches)
-    rep = os.path.join(src, f"prof_subpath_{tag}.ncu-rep")
+    rep = os.path.join(src, f"prof_{label or 'subpath'}_{tag}.ncu-rep")
     if not os.path.exists(rep):
         rep = os.path.join(src, f"prof_keyed_{tag}.ncu-rep")
     if os.path.exists(rep):
@@ -77,6 +78,10 @@ def main():
                     "smsp__thread_inst_executed_per_inst_executed.ratio",
                     "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
                     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+                    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                    "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                    "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+                    "smsp__warps_eligible.avg.per_cycle_active",
                     "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum"):
             if key in metrics:
                 keep[key] = {"unit": metrics[key][0], "value": metrics[key][1]}
@@ -108,6 +113,8 @@ def main():
                 regions.append(dict(first_sass_index=i, share=c / total, avg_lanes=t / c,
                                     first_instruction=chunk[0]["Source"].strip()))
         summary["full_capture"]["hot_regions_64_instr"] = regions
+    if label:
+        tag = f"{tag}_{label}"
     json.dump(summary, open(os.path.join(out_dir, f"{tag}_summary.json"), "w"), indent=1)
     # what bench.py quotes next to its live numbers (roofline.traffic, roofline.ncu)
     quoted_path = os.path.join(out_dir, "ncu_summary.json")
@@ -120,7 +127,7 @@ def main():
             "per_kernel_per_launch": {k: (v["dram_read_bytes"] + v["dram_write_bytes"]) / max(1, v["launches"]) for k, v in ours.items()},
             "source": f"profiles/{tag}_launches.csv: ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum over every "
                       f"path-tracing launch of one full-size step (640x480 @ 256 spp)"}
-    if "full_capture" in summary:
+    if "full_capture" in summary and not label:
         m = summary["full_capture"]["metrics"]
         quoted["latest_full_capture"] = {
             "source": f"profiles/{tag}_summary.json (ncu --set full of {m['Kernel Name']['value'].strip()}, BENCH_SPP=16 launch of the bench workload)",
@@ -132,7 +139,8 @@ def main():
             "warps_active_pct_of_peak": num(m["sm__warps_active.avg.pct_of_peak_sustained_active"]["value"]),
             "registers_per_thread": num(m["launch__registers_per_thread"]["value"])}
     quoted.pop("dram_bytes_per_launch", None)
-    json.dump(quoted, open(quoted_path, "w"), indent=1)
+    if not label:
+        json.dump(quoted, open(quoted_path, "w"), indent=1)
     with open(os.path.join(out_dir, f"{tag}_summary.md"), "w") as md:
         md.write(f"# ncu summary {tag}\n\n")
         if "launch_list" in summary:
