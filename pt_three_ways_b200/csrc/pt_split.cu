@@ -766,16 +766,7 @@ static cudaError_t launchSplitDual(const SplitArgs &args, int numSms, cudaStream
   if (err != cudaSuccess)
     return err;
   const bool deep = args.maxDepth - 2 > LevelStack<false>::kLevels || args.numMaterials > 0x8000u;
-  err = deep ? launchSubPathsDual<kBlock, true>(args, numSms, stream) : launchSubPathsDual<kBlock, false>(args, numSms, stream);
-  if (err != cudaSuccess)
-    return err;
-  const int block = 128;
-  const unsigned grid = (args.ownPixels + block - 1) / block;
-  if (args.numSub == 16)
-    resolveSamplesKernel<16><<<grid, block, 0, stream>>>(args);
-  else
-    resolveSamplesKernel<0><<<grid, block, 0, stream>>>(args);
-  return cudaGetLastError();
+  return deep ? launchSubPathsDual<kBlock, true>(args, numSms, stream) : launchSubPathsDual<kBlock, false>(args, numSms, stream);
 }
 
 template <int kBlock, int kMinBlocks, int kSweep>
@@ -784,11 +775,14 @@ static cudaError_t launchSplitShape(const SplitArgs &args, int numSms, cudaStrea
   if (err != cudaSuccess)
     return err;
   const bool deep = args.maxDepth - 2 > LevelStack<false>::kLevels || args.numMaterials > 0x8000u;
-  err = deep ? launchSubPaths<kBlock, kMinBlocks, kSweep, true>(args, numSms, stream)
-             : launchSubPaths<kBlock, kMinBlocks, kSweep, false>(args, numSms, stream);
-  if (err != cudaSuccess)
-    return err;
-  const int block = 128;
+  return deep ? launchSubPaths<kBlock, kMinBlocks, kSweep, true>(args, numSms, stream)
+              : launchSubPaths<kBlock, kMinBlocks, kSweep, false>(args, numSms, stream);
+}
+
+// The third kernel, on its own: blocks of 64 threads (2 304 registers) fit next to the three resident
+// CTAs of the NEXT batch's sub-path kernel, so that resolving one batch overlaps tracing the next.
+cudaError_t launchSplitResolve(const SplitArgs &args, cudaStream_t stream) {
+  const int block = 64;
   const unsigned grid = (args.ownPixels + block - 1) / block;
   if (args.numSub == 16)
     resolveSamplesKernel<16><<<grid, block, 0, stream>>>(args);
@@ -802,7 +796,8 @@ static cudaError_t launchSplitShape(const SplitArgs &args, int numSms, cudaStrea
 // moment form); launch
 // shapes of the sub-path kernel 0 = 256 threads x 2 CTAs/SM, 2 = 256 x 3, 3 = 192 x 4, 4 = 128 x 5,
 // 6 = 256 x 4.
-cudaError_t launchRenderSplit(const SplitArgs &args, int numSms, int config, cudaStream_t stream) {
+// Camera hits + sub-paths of one batch (two launches); launchSplitResolve() finishes it.
+cudaError_t launchSplitTrace(const SplitArgs &args, int numSms, int config, cudaStream_t stream) {
   switch (config) {
   case 207: return launchSplitDual<384>(args, numSms, stream);
   case 217: return launchSplitDual<512>(args, numSms, stream);

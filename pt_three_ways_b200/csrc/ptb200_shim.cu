@@ -59,7 +59,7 @@ constexpr size_t kSequentialSampleBufferBytes = size_t(4) << 30;
 constexpr size_t kSampleBufferBytes = size_t(1) << 30;
 // Keyed pipeline: records + strata terms of one batch of passes (pt_split.cu), ~530 B per sample
 // at 4x4 strata.  Batches of ~2 M samples keep the persistent sub-path kernel's tail below 1 %.
-constexpr size_t kSplitBufferBytes = size_t(1) << 30;
+constexpr size_t kSplitBufferBytes = size_t(1) << 30; // per buffer set; there are two
 
 // ---- host restatement of the per-triangle values the reference derives in addTriangle ----
 struct H3 {
@@ -156,11 +156,19 @@ struct PtContext {
   DeviceBuffer<PtPixelDevice> accumulator;
   DeviceBuffer<double> samples;
   DeviceBuffer<uint32_t> mtHistory;          // fp way: scratch of the per-lane engines (pt_mt19937.cuh)
-  DeviceBuffer<double2> records;             // keyed pipeline: camera-ray hits of one batch (pt_split.cu)
-  DeviceBuffer<double> terms;                //   ... one term per (sample, stratum)
-  DeviceBuffer<uint8_t> sampleKind;          //   ... strata terms / colour
+  // Keyed pipeline (pt_split.cu): batches alternate between two buffer sets on two streams, so that
+  // the next batch's tracing kernels overlap this batch's tail and its resolve kernel.
+  struct SplitSet {
+    DeviceBuffer<double2> records;             // camera-ray hits of one batch
+    DeviceBuffer<double> terms;                // one term per (sample, stratum)
+    DeviceBuffer<uint8_t> sampleKind;          // strata terms / colour
+    DeviceBuffer<unsigned long long> counters; // [0] ticket, [1] casts, [2] records of the batch
+    cudaStream_t stream{nullptr};
+    cudaEvent_t traced{nullptr}, resolved{nullptr};
+  } split[2];
+  cudaEvent_t splitReady{nullptr};
   uint32_t numMaterials{0};
-  DeviceBuffer<unsigned long long> counters; // [0] ticket, [1] casts, [2] records of the batch
+  DeviceBuffer<unsigned long long> counters; // [0] ticket, [1] casts (one-kernel forms)
   int accWidth{0}, accHeight{0};
 };
 
@@ -302,9 +310,15 @@ int ptb200_context_create(int32_t device, PtContext **out) {
     delete ctx;
     return fail(PTB200_ECUDA, "cudaStreamCreate failed");
   }
-  if (ctx->counters.ensure(3) != cudaSuccess) {
-    cudaStreamDestroy(ctx->stream);
-    delete ctx;
+  bool ok = ctx->counters.ensure(3) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ctx->splitReady, cudaEventDisableTiming) == cudaSuccess;
+  for (auto &set : ctx->split)
+    ok = ok && set.counters.ensure(3) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&set.stream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&set.traced, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&set.resolved, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    ptb200_context_destroy(ctx);
     return fail(PTB200_ENOMEM, "device allocation failed");
   }
   *out = ctx;
@@ -315,6 +329,18 @@ void ptb200_context_destroy(PtContext *ctx) {
   if (!ctx)
     return;
   cudaSetDevice(ctx->device);
+  for (auto &set : ctx->split) {
+    if (set.stream) {
+      cudaStreamSynchronize(set.stream);
+      cudaStreamDestroy(set.stream);
+    }
+    if (set.traced)
+      cudaEventDestroy(set.traced);
+    if (set.resolved)
+      cudaEventDestroy(set.resolved);
+  }
+  if (ctx->splitReady)
+    cudaEventDestroy(ctx->splitReady);
   if (ctx->stream) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamDestroy(ctx->stream);
@@ -487,9 +513,12 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
   passesPerBatch = std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses));
   if (split) {
     const size_t samples = passesPerBatch * pixelsPerPass;
-    PT_CUDA(ctx->records.ensure(samples * 9));
-    PT_CUDA(ctx->terms.ensure(samples * numSub * 3));
-    PT_CUDA(ctx->sampleKind.ensure(samples));
+    const int sets = static_cast<size_t>(numPasses) > passesPerBatch ? 2 : 1;
+    for (int k = 0; k < sets; ++k) {
+      PT_CUDA(ctx->split[k].records.ensure(samples * 9));
+      PT_CUDA(ctx->split[k].terms.ensure(samples * numSub * 3));
+      PT_CUDA(ctx->split[k].sampleKind.ensure(samples));
+    }
   } else {
     PT_CUDA(ctx->samples.ensure(passesPerBatch * pixelsPerPass * 3));
   }
@@ -515,6 +544,7 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       return rc;
   }
 
+  int splitBatch = 0;
   for (int done = 0; done < numPasses;) {
     const int batch = static_cast<int>(std::min<size_t>(passesPerBatch, static_cast<size_t>(numPasses - done)));
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -541,8 +571,14 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.castCounter = ctx->counters.ptr + 1;
       PT_CUDA(launchRenderSequential(a, ctx->stream));
     } else if (split) {
-      PT_CUDA(cudaMemsetAsync(ctx->counters.ptr, 0, sizeof(unsigned long long), ctx->stream));     // ticket
-      PT_CUDA(cudaMemsetAsync(ctx->counters.ptr + 2, 0, sizeof(unsigned long long), ctx->stream)); // records
+      // Batch b traces on the stream of buffer set b % 2 — after the resolve that last read the set
+      // — and resolves on ctx->stream, in batch order: passes are added in pass order.
+      PtContext::SplitSet &set = ctx->split[splitBatch & 1];
+      if (splitBatch == 0)
+        PT_CUDA(cudaEventRecord(ctx->splitReady, ctx->stream)); // scene, filter, accumulator are ready
+      PT_CUDA(cudaStreamWaitEvent(set.stream, splitBatch < 2 ? ctx->splitReady : set.resolved, 0));
+      PT_CUDA(cudaMemsetAsync(set.counters.ptr, 0, sizeof(unsigned long long), set.stream));     // ticket
+      PT_CUDA(cudaMemsetAsync(set.counters.ptr + 2, 0, sizeof(unsigned long long), set.stream)); // records
       SplitArgs a{};
       a.scene = ctx->scene;
       a.camera = toDeviceCamera(*camera);
@@ -569,17 +605,21 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.firstBounceVPow2 = (a.firstBounceV & (a.firstBounceV - 1)) == 0;
       a.invFirstBounceU = 1.0 / static_cast<double>(a.firstBounceU);
       a.invFirstBounceV = 1.0 / static_cast<double>(a.firstBounceV);
-      a.records = ctx->records.ptr;
-      a.terms = ctx->terms.ptr;
-      a.sampleKind = ctx->sampleKind.ptr;
-      a.counters = ctx->counters.ptr;
+      a.records = set.records.ptr;
+      a.terms = set.terms.ptr;
+      a.sampleKind = set.sampleKind.ptr;
+      a.counters = set.counters.ptr;
       a.accumulator = ctx->accumulator.ptr;
       if (keyedConfig % 10 >= 8) {
         if (!ctx->momentHostValid)
-          return fail(PTB200_EINVAL, "sweep variant 9 needs a scene of at most 64 triangles");
+          return fail(PTB200_EINVAL, "sweep variants 8/9 need a scene of at most 64 triangles");
         a.momentTable = ctx->momentHost;
       }
-      PT_CUDA(launchRenderSplit(a, ctx->numSms, keyedConfig, ctx->stream));
+      PT_CUDA(launchSplitTrace(a, ctx->numSms, keyedConfig, set.stream));
+      PT_CUDA(cudaEventRecord(set.traced, set.stream));
+      PT_CUDA(cudaStreamWaitEvent(ctx->stream, set.traced, 0));
+      PT_CUDA(launchSplitResolve(a, ctx->stream));
+      PT_CUDA(cudaEventRecord(set.resolved, ctx->stream));
       if (events) { // the three kernels of the pipeline are the path-tracing time
         PT_CUDA(cudaEventRecord(e1, ctx->stream));
         events->push_back(e0);
@@ -587,6 +627,7 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       }
       if (launches)
         *launches += 3;
+      ++splitBatch;
       done += batch;
       continue;
     } else {
@@ -659,6 +700,8 @@ int ptb200_context_render(PtContext *ctx, const PtCamera *camera, const PtRender
   ctx->accWidth = params->width;
   ctx->accHeight = params->height;
   PT_CUDA(cudaMemsetAsync(ctx->counters.ptr + 1, 0, sizeof(unsigned long long), ctx->stream));
+  for (auto &set : ctx->split) // the cast counters of this call (the sets' streams start after ctx->stream's event)
+    PT_CUDA(cudaMemsetAsync(set.counters.ptr + 1, 0, sizeof(unsigned long long), ctx->stream));
 
   EventList owned;
   cudaEvent_t begin = nullptr, end = nullptr;
@@ -683,7 +726,11 @@ int ptb200_context_render(PtContext *ctx, const PtCamera *camera, const PtRender
       sweepMs += part;
     }
     unsigned long long casts = 0;
-    PT_CUDA(cudaMemcpy(&casts, ctx->counters.ptr + 1, sizeof casts, cudaMemcpyDeviceToHost));
+    for (const unsigned long long *counter : {ctx->counters.ptr + 1, ctx->split[0].counters.ptr + 1, ctx->split[1].counters.ptr + 1}) {
+      unsigned long long part = 0;
+      PT_CUDA(cudaMemcpy(&part, counter, sizeof part, cudaMemcpyDeviceToHost));
+      casts += part;
+    }
     const PtRenderOptions defaults{};
     const PtRenderOptions &opt = options ? *options : defaults;
     const int rowStep = opt.rowStep > 0 ? opt.rowStep : 1;
