@@ -174,6 +174,15 @@ int ptb200_render_multi(const PtScene *scene, const PtCamera *camera,
                         const int32_t *devices, int32_t numDevices, PtPixel *out,
                         PtStats *stats);
 
+/* ptb200_render_multi with the progress callback of ptb200_render: in the pixel-parallel policies
+ * the passes are rendered in slices, every device renders a slice concurrently and `progress`
+ * sees the whole partial frame on the calling thread between slices (Scene.cpp:242-245); in the
+ * sequential policies (passes shared out between the devices) it is called once, at the end. */
+int ptb200_render_multi_progress(const PtScene *scene, const PtCamera *camera,
+                                 const PtRenderParams *params, const PtRenderOptions *options,
+                                 const int32_t *devices, int32_t numDevices, PtPixel *out,
+                                 PtProgressFn progress, void *user, PtStats *stats);
+
 /* Replaces dod::Scene::intersect (which=0), intersectSpheres (1), intersectTriangles (2);
  * nearerThan applies to 1 and 2.  rays: numRays x 6 doubles (origin, unit direction). */
 int ptb200_intersect(const PtScene *scene, int32_t device, int32_t which, double nearerThan,

@@ -22,6 +22,7 @@ RNG_MT19937_SEQUENTIAL_OO = 3  # the reference's `oo` way
 
 EXPORTS = [
     "ptb200_last_error", "ptb200_device_count", "ptb200_render", "ptb200_render_multi",
+    "ptb200_render_multi_progress",
     "ptb200_intersect", "ptb200_context_create", "ptb200_context_destroy",
     "ptb200_context_upload_scene", "ptb200_context_render", "ptb200_context_download",
     "ptb200_measure_fp64_peak", "ptb200_measure_fp32_peak",
@@ -113,6 +114,10 @@ def lib() -> C.CDLL:
                                              C.POINTER(PtRenderParams),
                                              C.POINTER(PtRenderOptions), C.c_void_p, C.c_int32,
                                              C.c_void_p, C.POINTER(PtStats)]
+        _lib.ptb200_render_multi_progress.argtypes = [C.POINTER(PtScene), C.POINTER(PtCamera),
+                                                      C.POINTER(PtRenderParams),
+                                                      C.POINTER(PtRenderOptions), C.c_void_p, C.c_int32,
+                                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PtStats)]
         _lib.ptb200_intersect.argtypes = [C.POINTER(PtScene), C.c_int32, C.c_int32, C.c_double,
                                           C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.ptb200_measure_fp64_peak.argtypes = [C.c_int32, C.POINTER(C.c_double),
@@ -187,14 +192,12 @@ def render(scene, camera18, params: PtRenderParams, options: PtRenderOptions | N
         raise ValueError("out must be a C-contiguous (height, width) PIXEL_DTYPE array")
     st = PtStats()
     if devices is not None:
-        if devices == "all":
-            _check(lib().ptb200_render_multi(C.byref(m.abi), C.byref(cam), C.byref(params),
-                                             C.byref(opts), None, 0, out.ctypes.data, C.byref(st)))
-        else:
-            arr = np.asarray(devices, dtype=np.int32)
-            _check(lib().ptb200_render_multi(C.byref(m.abi), C.byref(cam), C.byref(params),
-                                             C.byref(opts), arr.ctypes.data, arr.shape[0],
-                                             out.ctypes.data, C.byref(st)))
+        cb = PROGRESS_FN(progress) if progress else None
+        arr = None if devices == "all" else np.asarray(devices, dtype=np.int32)
+        _check(lib().ptb200_render_multi_progress(C.byref(m.abi), C.byref(cam), C.byref(params), C.byref(opts),
+                                                  None if arr is None else arr.ctypes.data,
+                                                  0 if arr is None else arr.shape[0], out.ctypes.data, cb, None,
+                                                  C.byref(st)))
     else:
         cb = PROGRESS_FN(progress) if progress else None
         _check(lib().ptb200_render(C.byref(m.abi), C.byref(cam), C.byref(params), C.byref(opts),

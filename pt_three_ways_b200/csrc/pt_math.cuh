@@ -41,6 +41,9 @@ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
 static __device__ __noinline__ double ieeeSqrt(double x) { return sqrt(x); }
 static __device__ __noinline__ double ieeeDiv(double a, double b) { return a / b; }
 static __device__ __noinline__ double ieeeRcpSqrt(double x) { return 1.0 / sqrt(x); }
+// Two independent square roots in one call: the same correctly rounded results, two Newton chains
+// to interleave (hemisphereSample's sqrt(v) and sqrt(1 - v), Samples.cpp:23,28).
+static __device__ __noinline__ double2 ieeeSqrtPair(double a, double b) { return make_double2(sqrt(a), sqrt(b)); }
 
 // Vec3::normalised (src/math/Vec3.impl.h:5-7): *this / length(), and operator/ multiplies by
 // the reciprocal (src/math/Vec3.h:51-54).
@@ -150,6 +153,34 @@ static __device__ __noinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, u
     k1 += 0xBB67AE85u;
   }
   return Philox4{{c0, c1, c2, c3}};
+}
+
+// Two blocks that differ in their last counter word only (c3 = 0 and 1: what one bounce or one camera
+// ray draws), advanced together: one key schedule, one call, two independent chains to interleave.
+struct Philox8 {
+  uint32_t w[8];
+};
+static __device__ __noinline__ Philox8 philox4x32_10_pair(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0,
+                                                           uint32_t k1) {
+  uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = 0u, b0 = c0, b1 = c1, b2 = c2, b3 = 1u;
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t ahi0 = __umulhi(0xD2511F53u, a0), alo0 = 0xD2511F53u * a0;
+    const uint32_t ahi1 = __umulhi(0xCD9E8D57u, a2), alo1 = 0xCD9E8D57u * a2;
+    const uint32_t bhi0 = __umulhi(0xD2511F53u, b0), blo0 = 0xD2511F53u * b0;
+    const uint32_t bhi1 = __umulhi(0xCD9E8D57u, b2), blo1 = 0xCD9E8D57u * b2;
+    a0 = ahi1 ^ a1 ^ k0;
+    a2 = ahi0 ^ a3 ^ k1;
+    a1 = alo1;
+    a3 = alo0;
+    b0 = bhi1 ^ b1 ^ k0;
+    b2 = bhi0 ^ b3 ^ k1;
+    b1 = blo1;
+    b3 = blo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return Philox8{{a0, a1, a2, a3, b0, b1, b2, b3}};
 }
 
 // ---- shading helpers --------------------------------------------------------------------

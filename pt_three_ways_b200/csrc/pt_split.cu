@@ -381,8 +381,9 @@ __device__ __forceinline__ void bounceSubPath(const SplitArgs &args, SubPath<kDe
       frameX = mk(q4.y, q5.x, q5.y);
       frameY = mk(q6.x, q6.y, q7.x);
     }
-    radius = ieeeSqrt(v);
-    zScale = ieeeSqrt(1 - v);
+    const double2 roots = ieeeSqrtPair(v, 1 - v);
+    radius = roots.x;
+    zScale = roots.y;
   }
   if (!direct) {
     double sinT, cosT;

@@ -128,21 +128,19 @@ struct KeyedDraws {
   uint32_t key0;
   __device__ __forceinline__ void camera(uint32_t pixel, double &a, double &b, double &c,
                                          double &d) const {
-    const Philox4 w0 = philox4x32_10(pixel, 0u, 0u, 0u, key0, kPhiloxKeyHigh);
-    const Philox4 w1 = philox4x32_10(pixel, 0u, 0u, 1u, key0, kPhiloxKeyHigh);
-    a = canonicalFromWords(w0.w[0], w0.w[1]);
-    b = canonicalFromWords(w0.w[2], w0.w[3]);
-    c = canonicalFromWords(w1.w[0], w1.w[1]);
-    d = canonicalFromWords(w1.w[2], w1.w[3]);
+    const Philox8 w = philox4x32_10_pair(pixel, 0u, 0u, key0, kPhiloxKeyHigh);
+    a = canonicalFromWords(w.w[0], w.w[1]);
+    b = canonicalFromWords(w.w[2], w.w[3]);
+    c = canonicalFromWords(w.w[4], w.w[5]);
+    d = canonicalFromWords(w.w[6], w.w[7]);
   }
   // The (u, v, p) triple of the radiance() call at `depth` in sub-path `subPath`.
   __device__ __forceinline__ void bounce(uint32_t pixel, uint32_t subPath, uint32_t depth,
                                          double &u, double &v, double &p) const {
-    const Philox4 w0 = philox4x32_10(pixel, subPath, depth + 1u, 0u, key0, kPhiloxKeyHigh);
-    const Philox4 w1 = philox4x32_10(pixel, subPath, depth + 1u, 1u, key0, kPhiloxKeyHigh);
-    u = canonicalFromWords(w0.w[0], w0.w[1]);
-    v = canonicalFromWords(w0.w[2], w0.w[3]);
-    p = canonicalFromWords(w1.w[0], w1.w[1]);
+    const Philox8 w = philox4x32_10_pair(pixel, subPath, depth + 1u, key0, kPhiloxKeyHigh);
+    u = canonicalFromWords(w.w[0], w.w[1]);
+    v = canonicalFromWords(w.w[2], w.w[3]);
+    p = canonicalFromWords(w.w[4], w.w[5]);
   }
 };
 

@@ -848,6 +848,12 @@ int ptb200_render(const PtScene *scene, const PtCamera *camera, const PtRenderPa
 int ptb200_render_multi(const PtScene *scene, const PtCamera *camera, const PtRenderParams *params,
                         const PtRenderOptions *options, const int32_t *devices, int32_t numDevices,
                         PtPixel *out, PtStats *stats) {
+  return ptb200_render_multi_progress(scene, camera, params, options, devices, numDevices, out, nullptr, nullptr, stats);
+}
+
+int ptb200_render_multi_progress(const PtScene *scene, const PtCamera *camera, const PtRenderParams *params,
+                                 const PtRenderOptions *options, const int32_t *devices, int32_t numDevices,
+                                 PtPixel *out, PtProgressFn progress, void *user, PtStats *stats) {
   if (!camera || !out)
     return fail(PTB200_EINVAL, "null argument");
   if (const int rc = validateParams(params, options))
@@ -868,62 +874,150 @@ int ptb200_render_multi(const PtScene *scene, const PtCamera *camera, const PtRe
     return fail(PTB200_EINVAL, "render_multi partitions rows itself; leave rowBegin/rowStep zero");
   const int n = static_cast<int>(list.size());
   const size_t pixels = static_cast<size_t>(params->width) * params->height;
+  const int spp = params->samplesPerPixel;
   const bool sequential = base.rngMode == PTB200_RNG_MT19937_SEQUENTIAL ||
                           base.rngMode == PTB200_RNG_MT19937_SEQUENTIAL_OO;
+  PtStats total{};
 
-  struct Part {
-    std::vector<PtPixel> pixels;
-    PtStats stats{};
-    int rc{PTB200_OK};
-    char error[512]{};
-  };
-  std::vector<Part> parts(n);
-  std::vector<std::thread> threads;
-  for (int g = 0; g < n; ++g) {
-    threads.emplace_back([&, g] {
-      Part &part = parts[g];
-      part.pixels.assign(pixels, PtPixel{});
-      PtRenderOptions opt = base;
-      PtRenderParams prm = *params;
-      opt.device = list[g];
-      if (sequential) { // passes s with s % n == g, as contiguous blocks
-        const int spp = params->samplesPerPixel;
+  if (sequential) {
+    // One engine per pass walks the whole frame: only passes can be shared out (contiguous blocks,
+    // one per device), each device renders a full frame and the frames are added in device order —
+    // the operator+= the reference applies to per-pass outputs (ArrayOutput.cpp:48-56).
+    struct Part {
+      std::vector<PtPixel> pixels;
+      PtStats stats{};
+      int rc{PTB200_OK};
+      char error[512]{};
+    };
+    std::vector<Part> parts(n);
+    std::vector<std::thread> threads;
+    for (int g = 0; g < n; ++g) {
+      threads.emplace_back([&, g] {
+        Part &part = parts[g];
+        part.pixels.assign(pixels, PtPixel{});
+        PtRenderOptions opt = base;
+        PtRenderParams prm = *params;
+        opt.device = list[g];
         const int lo = static_cast<int>(static_cast<long long>(spp) * g / n);
         const int hi = static_cast<int>(static_cast<long long>(spp) * (g + 1) / n);
         opt.passBegin = base.passBegin + lo;
         prm.samplesPerPixel = hi - lo;
-      } else { // rows y with y % n == g
-        opt.rowBegin = g;
-        opt.rowStep = n;
-      }
-      part.rc = ptb200_render(scene, camera, &prm, &opt, part.pixels.data(), nullptr, nullptr, &part.stats);
-      if (part.rc)
-        snprintf(part.error, sizeof part.error, "%s", ptb200_last_error());
-    });
-  }
-  for (auto &t : threads)
-    t.join();
-  PtStats total{};
-  for (int g = 0; g < n; ++g) {
-    if (parts[g].rc)
-      return fail(parts[g].rc, "device %d: %s", list[g], parts[g].error);
-    total.samples += parts[g].stats.samples;
-    total.casts += parts[g].stats.casts;
-    total.kernelLaunches += parts[g].stats.kernelLaunches;
-    total.kernelMs = std::max(total.kernelMs, parts[g].stats.kernelMs);
-    total.sweepKernelMs = std::max(total.sweepKernelMs, parts[g].stats.sweepKernelMs);
-  }
-  // Host-side gather: device order, i.e. for sequential mode ascending pass blocks (the same
-  // operator+= the reference applies to per-pass outputs, ArrayOutput.cpp:48-56).
-  std::memset(out, 0, pixels * sizeof(PtPixel));
-  for (int g = 0; g < n; ++g) {
-    for (size_t i = 0; i < pixels; ++i) {
-      out[i].sum[0] += parts[g].pixels[i].sum[0];
-      out[i].sum[1] += parts[g].pixels[i].sum[1];
-      out[i].sum[2] += parts[g].pixels[i].sum[2];
-      out[i].numSamples += parts[g].pixels[i].numSamples;
+        part.rc = ptb200_render(scene, camera, &prm, &opt, part.pixels.data(), nullptr, nullptr, &part.stats);
+        if (part.rc)
+          snprintf(part.error, sizeof part.error, "%s", ptb200_last_error());
+      });
     }
+    for (auto &t : threads)
+      t.join();
+    for (int g = 0; g < n; ++g) {
+      if (parts[g].rc)
+        return fail(parts[g].rc, "device %d: %s", list[g], parts[g].error);
+      total.samples += parts[g].stats.samples;
+      total.casts += parts[g].stats.casts;
+      total.kernelLaunches += parts[g].stats.kernelLaunches;
+      total.kernelMs = std::max(total.kernelMs, parts[g].stats.kernelMs);
+      total.sweepKernelMs = std::max(total.sweepKernelMs, parts[g].stats.sweepKernelMs);
+    }
+    std::memset(out, 0, pixels * sizeof(PtPixel));
+    for (int g = 0; g < n; ++g) {
+      for (size_t i = 0; i < pixels; ++i) {
+        out[i].sum[0] += parts[g].pixels[i].sum[0];
+        out[i].sum[1] += parts[g].pixels[i].sum[1];
+        out[i].sum[2] += parts[g].pixels[i].sum[2];
+        out[i].numSamples += parts[g].pixels[i].numSamples;
+      }
+    }
+    if (progress)
+      progress(user, out, spp, spp);
+    if (stats)
+      *stats = total;
+    return PTB200_OK;
   }
+
+  // Pixel-parallel policies: device g owns the rows y % n == g for every pass and copies exactly
+  // those rows into the caller's frame — the final gather needs no arithmetic.  With a progress
+  // callback the passes are rendered in slices: all devices render a slice concurrently, then the
+  // callback sees the whole partial frame on the CALLING thread (Scene.cpp:242-245).
+  struct Device {
+    PtContext *ctx{nullptr};
+    PtStats slice{};
+    int rc{PTB200_OK};
+    char error[512]{};
+  };
+  std::vector<Device> devs(n);
+  auto onEveryDevice = [&](auto &&body) {
+    std::vector<std::thread> threads;
+    for (int g = 0; g < n; ++g)
+      threads.emplace_back([&, g] {
+        devs[g].rc = body(g);
+        if (devs[g].rc)
+          snprintf(devs[g].error, sizeof devs[g].error, "%s", ptb200_last_error());
+      });
+    for (auto &t : threads)
+      t.join();
+    for (int g = 0; g < n; ++g)
+      if (devs[g].rc)
+        return g;
+    return -1;
+  };
+  auto release = [&](bool ok) {
+    for (Device &d : devs) {
+      if (!d.ctx)
+        continue;
+      if (ok)
+        poolGive(d.ctx);
+      else
+        ptb200_context_destroy(d.ctx);
+    }
+  };
+  int failed = onEveryDevice([&](int g) {
+    devs[g].ctx = poolTake(list[g]);
+    if (!devs[g].ctx) {
+      if (const int rc = ptb200_context_create(list[g], &devs[g].ctx))
+        return rc;
+    }
+    return ptb200_context_upload_scene(devs[g].ctx, scene);
+  });
+  const int step = progress && spp > 0 ? (base.passesPerBatch > 0 ? base.passesPerBatch : std::max(1, (spp + 19) / 20))
+                                       : std::max(spp, 1);
+  for (int done = 0; failed < 0 && done < std::max(spp, 1); done += step) {
+    const int passes = std::min(step, spp - done);
+    failed = onEveryDevice([&](int g) {
+      PtRenderOptions opt = base;
+      PtRenderParams prm = *params;
+      opt.device = list[g];
+      opt.rowBegin = g;
+      opt.rowStep = n;
+      opt.passBegin = base.passBegin + done;
+      prm.samplesPerPixel = passes;
+      devs[g].slice = PtStats{};
+      if (const int rc = ptb200_context_render(devs[g].ctx, camera, &prm, &opt, done > 0, &devs[g].slice))
+        return rc;
+      return downloadRows(devs[g].ctx, out, &opt);
+    });
+    if (failed >= 0)
+      break;
+    double kernelMs = 0, sweepMs = 0;
+    for (const Device &d : devs) {
+      total.samples += d.slice.samples;
+      total.casts += d.slice.casts;
+      total.kernelLaunches += d.slice.kernelLaunches;
+      kernelMs = std::max(kernelMs, d.slice.kernelMs);
+      sweepMs = std::max(sweepMs, d.slice.sweepKernelMs);
+    }
+    total.kernelMs += kernelMs;
+    total.sweepKernelMs += sweepMs;
+    if (progress && progress(user, out, done + passes, spp) != 0)
+      break;
+  }
+  if (failed >= 0) {
+    const int rc = devs[failed].rc;
+    char message[512];
+    snprintf(message, sizeof message, "%s", devs[failed].error);
+    release(false);
+    return fail(rc, "device %d: %s", list[failed], message);
+  }
+  release(true);
   if (stats)
     *stats = total;
   return PTB200_OK;

@@ -174,10 +174,11 @@ public:
 
     const bool multi = useAllDevices_ || deviceList_.size() > 1;
     if (multi) {
-      check(ptb200_render_multi(&m.scene, &camera.abi(), &params, &options_,
-                                deviceList_.empty() ? nullptr : deviceList_.data(),
-                                static_cast<int32_t>(deviceList_.size()), raw.data(), &lastStats_),
-            "ptb200_render_multi");
+      check(ptb200_render_multi_progress(&m.scene, &camera.abi(), &params, &options_,
+                                         deviceList_.empty() ? nullptr : deviceList_.data(),
+                                         static_cast<int32_t>(deviceList_.size()), raw.data(),
+                                         updateFunc ? +trampoline : nullptr, &forward, &lastStats_),
+            "ptb200_render_multi_progress");
     } else {
       check(ptb200_render(&m.scene, &camera.abi(), &params, &options_, raw.data(),
                           updateFunc ? +trampoline : nullptr, &forward, &lastStats_),
@@ -185,8 +186,6 @@ public:
     }
     ArrayOutput output(renderParams.width, renderParams.height);
     output.addSamples(raw.data());
-    if (updateFunc && multi)
-      updateFunc(output);
     return output;
   }
 

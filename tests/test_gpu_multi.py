@@ -46,3 +46,29 @@ def test_each_device_renders_the_same(scenes, capi):
     a, _ = capi.render(scene, cam, capi.make_params(w, h, spp=2, seed=9), capi.make_options(device=0))
     b, _ = capi.render(scene, cam, capi.make_params(w, h, spp=2, seed=9), capi.make_options(device=1))
     assert np.array_equal(a["sum"], b["sum"])
+
+
+def test_render_multi_forwards_progress_on_the_calling_thread(scenes, capi):
+    """ptb200_render_multi_progress: every device renders a slice of passes, the callback then sees
+    the WHOLE partial frame (all rows, n == passes so far) on the caller's thread; the final frame
+    equals the single-device render bit for bit."""
+    import threading
+    need_devices(capi, 2)
+    scene = scenes["cornell"]
+    w, h, spp = 48, 35, 10
+    cam = scene.camera(w, h)
+    seen = []
+
+    def progress(user, pixels, done, total):
+        arr = np.ctypeslib.as_array((capi.C.c_uint8 * (w * h * 32)).from_address(pixels)).view(capi.PIXEL_DTYPE)
+        seen.append((threading.get_ident(), done, total, int(arr["n"].min()), int(arr["n"].max())))
+        return 0
+
+    multi, st = capi.render(scene, cam, capi.make_params(w, h, spp=spp, seed=4),
+                            capi.make_options(passes_per_batch=4), progress=progress, devices=[0, 1])
+    assert [s[1] for s in seen] == [4, 8, 10] and all(s[2] == spp for s in seen)
+    assert all(s[0] == threading.get_ident() for s in seen)
+    assert all(s[3] == s[4] == s[1] for s in seen)
+    single, st1 = capi.render(scene, cam, capi.make_params(w, h, spp=spp, seed=4))
+    assert np.array_equal(multi["sum"], single["sum"]) and np.array_equal(multi["n"], single["n"])
+    assert st["casts"] == st1["casts"] and st["samples"] == st1["samples"]

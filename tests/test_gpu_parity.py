@@ -235,6 +235,18 @@ def test_progress_callback_runs_on_calling_thread_with_partial_frames(scenes, ca
     assert np.array_equal(final["sum"], ref["sum"])
 
 
+def test_zero_samples_with_a_progress_callback_returns_an_empty_frame(scenes, capi):
+    """spp == 0 through the progressive path of a pooled context: the frame of THIS call,
+    all zero, not the previous call's accumulator."""
+    scene = scenes["cornell"]
+    big, _ = capi.render(scene, scene.camera(40, 30), capi.make_params(40, 30, spp=2, seed=1))
+    assert (big["n"] == 2).all()
+    calls = []
+    px, st = capi.render(scene, scene.camera(16, 12), capi.make_params(16, 12, spp=0, seed=1),
+                         progress=lambda user, pixels, done, total: calls.append(done) or 0)
+    assert st["samples"] == 0 and (px["n"] == 0).all() and (px["sum"] == 0).all()
+
+
 @pytest.mark.parametrize("scene_name,w,h", [("suzanne", 96, 72), ("cornell", 128, 96), ("ce", 16, 9)])
 def test_every_megakernel_configuration_renders_identically(scene_name, w, h, scenes, tmp_path):
     """Every render-kernel instantiation — the one-kernel form (1, 6, 26) and the three-kernel
