@@ -629,6 +629,54 @@ __device__ __forceinline__ void sweepTileStage0Moment(const float *__restrict__ 
   }
 }
 
+// stage0RejectMoment4() for TWO rays, interleaved component by component: each float4 of the group is
+// used for both rays right after it is loaded, so only the twelve running sums (two rays x two pairs
+// x {det, X, Y}) stay live instead of the whole 19-vector group.
+struct Stage0Sums {
+  float2 detL, detH, xL, xH, yL, yH;
+};
+__device__ __forceinline__ void stage0Accumulate(Stage0Sums &s, const MomentRay &r, int k, float4 a) {
+  const float2 lo = make_float2(a.x, a.y), hi = make_float2(a.z, a.w);
+  // k: 0-2 det (d . nn), 3-8 X (m . e2 + d . a2), 9-14 Y (m . -e1 + d . -a1)
+  const float w = (k == 0 || k == 6 || k == 12) ? r.dx : (k == 1 || k == 7 || k == 13) ? r.dy
+                  : (k == 2 || k == 8 || k == 14) ? r.dz : (k == 3 || k == 9) ? r.mx
+                  : (k == 4 || k == 10) ? r.my : r.mz;
+  if (k == 0) {
+    s.detL = __fmul2_rn(splat(w), lo), s.detH = __fmul2_rn(splat(w), hi);
+  } else if (k < 3) {
+    s.detL = __ffma2_rn(splat(w), lo, s.detL), s.detH = __ffma2_rn(splat(w), hi, s.detH);
+  } else if (k == 3) {
+    s.xL = __fmul2_rn(splat(w), lo), s.xH = __fmul2_rn(splat(w), hi);
+  } else if (k < 9) {
+    s.xL = __ffma2_rn(splat(w), lo, s.xL), s.xH = __ffma2_rn(splat(w), hi, s.xH);
+  } else if (k == 9) {
+    s.yL = __fmul2_rn(splat(w), lo), s.yH = __fmul2_rn(splat(w), hi);
+  } else {
+    s.yL = __ffma2_rn(splat(w), lo, s.yL), s.yH = __ffma2_rn(splat(w), hi, s.yH);
+  }
+}
+__device__ __forceinline__ void stage0Decide(const Stage0Sums &s, const MomentRay &r, float4 ed, float4 kx, float4 ky,
+                                             float4 k3, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+  uint32_t s0, s1, s2, s3; // copysign(1, det)
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s0) : "r"(__float_as_uint(s.detL.x)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s1) : "r"(__float_as_uint(s.detL.y)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s2) : "r"(__float_as_uint(s.detH.x)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s3) : "r"(__float_as_uint(s.detH.y)), "r"(r.one));
+  const float2 sL = make_float2(__uint_as_float(s0), __uint_as_float(s1));
+  const float2 sH = make_float2(__uint_as_float(s2), __uint_as_float(s3));
+  const float2 adetL = make_float2(fabsf(s.detL.x), fabsf(s.detL.y)), adetH = make_float2(fabsf(s.detH.x), fabsf(s.detH.y));
+  const float2 fL = __fadd2_rn(make_float2(ed.x, ed.y), neg2(adetL)), fH = __fadd2_rn(make_float2(ed.z, ed.w), neg2(adetH));
+  const float2 aL = __ffma2_rn(s.xL, sL, make_float2(kx.x, kx.y)), aH = __ffma2_rn(s.xH, sH, make_float2(kx.z, kx.w));
+  const float2 bL = __ffma2_rn(s.yL, sL, make_float2(ky.x, ky.y)), bH = __ffma2_rn(s.yH, sH, make_float2(ky.z, ky.w));
+  const float2 boundL = __ffma2_rn(adetL, splat(1.0f + 0x1p-20f), make_float2(k3.x, k3.y));
+  const float2 boundH = __ffma2_rn(adetH, splat(1.0f + 0x1p-20f), make_float2(k3.z, k3.w));
+  const float2 eL = __ffma2_rn(neg2(__fadd2_rn(s.xL, s.yL)), sL, boundL), eH = __ffma2_rn(neg2(__fadd2_rn(s.xH, s.yH)), sH, boundH);
+  r0 = (__float_as_uint(aL.x) | __float_as_uint(bL.x) | __float_as_uint(eL.x)) & __float_as_uint(fL.x);
+  r1 = (__float_as_uint(aL.y) | __float_as_uint(bL.y) | __float_as_uint(eL.y)) & __float_as_uint(fL.y);
+  r2 = (__float_as_uint(aH.x) | __float_as_uint(bH.x) | __float_as_uint(eH.x)) & __float_as_uint(fH.x);
+  r3 = (__float_as_uint(aH.y) | __float_as_uint(bH.y) | __float_as_uint(eH.y)) & __float_as_uint(fH.y);
+}
+
 // The same sweep for TWO rays of one lane: every group of triangles is loaded once and tested
 // against both (the loads, not the arithmetic, bound the one-ray form: see subPathDualKernel).
 __device__ __forceinline__ void survivorsOfChunk(unsigned long long keep, const double *__restrict__ exact, int chunk,
@@ -655,18 +703,22 @@ __device__ __forceinline__ void sweepTileStage0Moment2(const float *__restrict__
     const float4 *const groupEnd = reinterpret_cast<const float4 *>(filter) + (chunkEnd >> 2) * kMomentFloats;
 #pragma unroll 1
     for (; group != groupEnd; group += kMomentFloats) {
-      float4 a[kMomentFloats];
+      Stage0Sums sums0, sums1;
 #pragma unroll
-      for (int k = 0; k < kMomentFloats; ++k)
-        a[k] = group[k];
+      for (int k = 0; k < 15; ++k) {
+        const float4 a = group[k];
+        stage0Accumulate(sums0, ray0, k, a);
+        stage0Accumulate(sums1, ray1, k, a);
+      }
+      const float4 ed = group[15], kx = group[16], ky = group[17], k3 = group[18];
       uint32_t r0, r1, r2, r3;
-      stage0RejectMoment4(a, ray0, r0, r1, r2, r3);
+      stage0Decide(sums0, ray0, ed, kx, ky, k3, r0, r1, r2, r3);
       hi0 = __funnelshift_l(lo0, hi0, 4);
       lo0 = __funnelshift_l(r0, lo0, 1);
       lo0 = __funnelshift_l(r1, lo0, 1);
       lo0 = __funnelshift_l(r2, lo0, 1);
       lo0 = __funnelshift_l(r3, lo0, 1);
-      stage0RejectMoment4(a, ray1, r0, r1, r2, r3);
+      stage0Decide(sums1, ray1, ed, kx, ky, k3, r0, r1, r2, r3);
       hi1 = __funnelshift_l(lo1, hi1, 4);
       lo1 = __funnelshift_l(r0, lo1, 1);
       lo1 = __funnelshift_l(r1, lo1, 1);

@@ -1028,9 +1028,10 @@ int chooseKeyedConfig(uint32_t numTriangles, bool filterUsable, int way) {
   if (filterUsable && numTriangles > 0 && constTableFits(numTriangles, 1))
     return 128;
   // scenes whose tile fills the shared memory are bound by its data pipe: two sub-paths per lane share
-  // every group of triangles they load (suzanne 40.0 -> 44.3, ce 3.65 -> 3.91 Msamples/s, r2h)
+  // every group of triangles they load (suzanne 40.0 -> 46.4, ce 3.65 -> 4.08 Msamples/s; one CTA of 512
+  // threads per SM at 128 registers)
   if (filterUsable && !small)
-    return 207;
+    return 217;
   return 100 + 10 * (small ? 2 : 0) + sweep;
 }
 
