@@ -793,8 +793,9 @@ cudaError_t launchSplitResolve(const SplitArgs &args, cudaStream_t stream) {
 }
 
 // A pipeline configuration is 100 + 10 * launchShape + sweepVariant (the megakernel's numbering
-// plus 100): sweep variants 1 (two-stage FP64), 6 (sign-bit FP32 stage 0 + exact) and 7 (the same in
-// moment form); launch
+// plus 100; 200 + ... = two sub-paths per lane): sweep variants 1 (two-stage FP64), 6 (sign-bit FP32
+// stage 0 + exact), 7 (the same in moment form), 8 (7 out of the constant bank, scenes of up to 64
+// triangles) and 9 (8 with the group loop unrolled); launch
 // shapes of the sub-path kernel 0 = 256 threads x 2 CTAs/SM, 2 = 256 x 3, 3 = 192 x 4, 4 = 128 x 5,
 // 6 = 256 x 4.
 // Camera hits + sub-paths of one batch (two launches); launchSplitResolve() finishes it.
@@ -809,12 +810,8 @@ cudaError_t launchSplitTrace(const SplitArgs &args, int numSms, int config, cuda
   case 126: return launchSplitShape<256, 3, 6>(args, numSms, stream);
   case 128: return launchSplitShape<256, 3, 8>(args, numSms, stream);
   case 168: return launchSplitShape<256, 4, 8>(args, numSms, stream);
-  case 188: return launchSplitShape<192, 5, 8>(args, numSms, stream);
   case 148: return launchSplitShape<128, 5, 8>(args, numSms, stream);
-  case 109: return launchSplitShape<256, 2, 9>(args, numSms, stream);
-  case 129: return launchSplitShape<256, 3, 9>(args, numSms, stream);
-  case 149: return launchSplitShape<128, 5, 9>(args, numSms, stream);
-  case 169: return launchSplitShape<256, 4, 9>(args, numSms, stream);
+  case 129: return launchSplitShape<256, 3, 9>(args, numSms, stream); // kept as the measured counter-example
   case 107: return launchSplitShape<256, 2, 7>(args, numSms, stream);
   case 127: return launchSplitShape<256, 3, 7>(args, numSms, stream);
   case 137: return launchSplitShape<192, 4, 7>(args, numSms, stream);
