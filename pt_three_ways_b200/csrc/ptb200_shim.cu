@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -149,6 +150,7 @@ struct PtContext {
   DeviceBuffer<float> triMoment;
   MomentTable momentHost{};    // host copy of triMoment for scenes whose table rides in the kernel parameters
   bool momentHostValid{false};
+  uint32_t fanGroups{0};       // groups of four triangles that are two quads in fan order (pt_device.cuh)
   DeviceBuffer<double> triExact;
   double sceneRadius{0};       // >= |p| for every vertex / sphere surface point
   double filterOriginBound{-1}; // origin bound the current triFilter contents were built for
@@ -400,6 +402,21 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
       longestEdge = std::max(longestEdge, std::sqrt(ex * ex + ey * ey + ez * ez));
     }
   }
+  // Groups of four consecutive triangles that are two quads in fan order: (v0, e1, e2), (v0, e2, e3)
+  // twice, compared as stored doubles (all-zero padding qualifies too).
+  ctx->fanGroups = 0;
+  if (d.numTiles == 1 && d.tileTris <= 4u * kConstGroups) {
+    auto value = [&](uint32_t tri, int k) { return tri < scene->numTriangles ? exact[10 * static_cast<size_t>(tri) + k] : 0.0; };
+    auto fanPair = [&](uint32_t a, uint32_t b) {
+      for (int k = 0; k < 3; ++k)
+        if (value(a, k) != value(b, k) || value(a, 6 + k) != value(b, 3 + k)) // same v0; e2 of A == e1 of B
+          return false;
+      return true;
+    };
+    for (uint32_t g = 0; g * 4 < d.tileTris; ++g)
+      if (fanPair(4 * g, 4 * g + 1) && fanPair(4 * g + 2, 4 * g + 3))
+        ctx->fanGroups |= 1u << g;
+  }
   ctx->sceneRadius = radius;
   ctx->filterUsable = std::isfinite(radius) && radius < 1e6 && longestEdge < 1e6;
   ctx->filterOriginBound = -1;
@@ -465,6 +482,13 @@ static int ensureFilter(PtContext *ctx, double originBound, uint64_t *launches) 
     PT_CUDA(cudaMemcpyAsync(&ctx->momentHost, ctx->triMoment.ptr, static_cast<size_t>(ctx->scene.tileTris) * 19 * sizeof(float),
                             cudaMemcpyDeviceToHost, ctx->stream));
     PT_CUDA(cudaStreamSynchronize(ctx->stream));
+    // Fan groups carry their lanes as [A0, A1, B0, B1]: swap the two middle triangles of every row.
+    const uint32_t usable = std::getenv("PTB200_NO_FAN_GROUPS") ? 0u : ctx->fanGroups;
+    for (int g = 0; g < kConstGroups; ++g)
+      if (usable & (1u << g))
+        for (float4 &row : ctx->momentHost.group[g])
+          std::swap(row.y, row.z);
+    ctx->momentHost.fanGroups = usable;
     ctx->momentHostValid = true;
   }
   if (launches && ctx->scene.numTiles)
