@@ -32,6 +32,8 @@ struct DeviceScene {
   const double *materials;    // [numMaterials][10] MaterialSpec order + 1/indexOfRefraction
   const float *triFilter;     // [numTiles][tileTris/4][14][4] fp32 stage-0 data (buildFilterKernel)
   const float *triMoment;     // [numTiles][tileTris/4][19][4] fp32 stage-0 data in moment (Pluecker) form
+  const uint32_t *fanMask;    // bit per group of four triangles (tile-major): the group is two quads in fan
+                              //   order and its triMoment lanes are stored [A0, A1, B0, B1] (stage0RejectFan4)
   const double *triExact;     // [numTiles*tileTris][10] AoS copy of the 9 sweep doubles (+pad) for the
                               //   survivors' exact test: one address, five 16-byte loads
   uint32_t numTriangles;
@@ -588,15 +590,73 @@ __device__ __forceinline__ void stage0RejectMoment4(const float4 (&a)[kMomentFlo
   r3 = (__float_as_uint(aH.y) | __float_as_uint(bH.y) | __float_as_uint(eH.y)) & __float_as_uint(fH.y);
 }
 
+// A quad face `f a b c d` reaches the scene as the fan (a,b,c), (a,c,d) (ObjLoaderImpl.h:75-85): triangle
+// B shares v0 with triangle A and its first edge IS A's second edge, bit for bit.  Then B's
+// Y numerator is A's X numerator negated —  Y_B = -e1_B.m - d.(v0 x e1_B) = -(e2_A.m + d.(v0 x e2_A))
+// = -X_A  — through the very same operations (negation commutes with rounding), so a group of two
+// such quads, packed as [A0, A1 | B0, B1], needs Y for its first pair only: 24 instead of 30 packed
+// operations and 32 instead of 38 constant loads per four triangles, the same decisions bit for bit.
+// The upload marks the groups that qualify (exact comparisons of the stored doubles).
+__device__ __forceinline__ void stage0RejectFan4(const float4 (&a)[kMomentFloats], const MomentRay &r,
+                                                 uint32_t &rA0, uint32_t &rA1, uint32_t &rB0, uint32_t &rB1) {
+#define PT_LO(k) make_float2(a[k].x, a[k].y)
+#define PT_HI(k) make_float2(a[k].z, a[k].w)
+  float2 detL = __fmul2_rn(splat(r.dx), PT_LO(0)), detH = __fmul2_rn(splat(r.dx), PT_HI(0));
+  detL = __ffma2_rn(splat(r.dy), PT_LO(1), detL), detH = __ffma2_rn(splat(r.dy), PT_HI(1), detH);
+  detL = __ffma2_rn(splat(r.dz), PT_LO(2), detL), detH = __ffma2_rn(splat(r.dz), PT_HI(2), detH);
+  float2 xL = __fmul2_rn(splat(r.mx), PT_LO(3)), xH = __fmul2_rn(splat(r.mx), PT_HI(3));
+  xL = __ffma2_rn(splat(r.my), PT_LO(4), xL), xH = __ffma2_rn(splat(r.my), PT_HI(4), xH);
+  xL = __ffma2_rn(splat(r.mz), PT_LO(5), xL), xH = __ffma2_rn(splat(r.mz), PT_HI(5), xH);
+  xL = __ffma2_rn(splat(r.dx), PT_LO(6), xL), xH = __ffma2_rn(splat(r.dx), PT_HI(6), xH);
+  xL = __ffma2_rn(splat(r.dy), PT_LO(7), xL), xH = __ffma2_rn(splat(r.dy), PT_HI(7), xH);
+  xL = __ffma2_rn(splat(r.dz), PT_LO(8), xL), xH = __ffma2_rn(splat(r.dz), PT_HI(8), xH);
+  float2 yL = __fmul2_rn(splat(r.mx), PT_LO(9));
+  yL = __ffma2_rn(splat(r.my), PT_LO(10), yL);
+  yL = __ffma2_rn(splat(r.mz), PT_LO(11), yL);
+  yL = __ffma2_rn(splat(r.dx), PT_LO(12), yL);
+  yL = __ffma2_rn(splat(r.dy), PT_LO(13), yL);
+  yL = __ffma2_rn(splat(r.dz), PT_LO(14), yL);
+  const float2 yH = neg2(xL); // the fan identity
+  uint32_t s0, s1, s2, s3; // copysign(1, det)
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s0) : "r"(__float_as_uint(detL.x)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s1) : "r"(__float_as_uint(detL.y)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s2) : "r"(__float_as_uint(detH.x)), "r"(r.one));
+  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s3) : "r"(__float_as_uint(detH.y)), "r"(r.one));
+  const float2 sL = make_float2(__uint_as_float(s0), __uint_as_float(s1));
+  const float2 sH = make_float2(__uint_as_float(s2), __uint_as_float(s3));
+  const float2 adetL = make_float2(fabsf(detL.x), fabsf(detL.y)), adetH = make_float2(fabsf(detH.x), fabsf(detH.y));
+  const float2 fL = __fadd2_rn(PT_LO(15), neg2(adetL)), fH = __fadd2_rn(PT_HI(15), neg2(adetH));
+  const float2 aL = __ffma2_rn(xL, sL, PT_LO(16)), aH = __ffma2_rn(xH, sH, PT_HI(16));
+  const float2 bL = __ffma2_rn(yL, sL, PT_LO(17)), bH = __ffma2_rn(yH, sH, PT_HI(17));
+  const float2 boundL = __ffma2_rn(adetL, splat(1.0f + 0x1p-20f), PT_LO(18));
+  const float2 boundH = __ffma2_rn(adetH, splat(1.0f + 0x1p-20f), PT_HI(18));
+  const float2 eL = __ffma2_rn(neg2(__fadd2_rn(xL, yL)), sL, boundL), eH = __ffma2_rn(neg2(__fadd2_rn(xH, yH)), sH, boundH);
+#undef PT_LO
+#undef PT_HI
+  rA0 = (__float_as_uint(aL.x) | __float_as_uint(bL.x) | __float_as_uint(eL.x)) & __float_as_uint(fL.x);
+  rA1 = (__float_as_uint(aL.y) | __float_as_uint(bL.y) | __float_as_uint(eL.y)) & __float_as_uint(fL.y);
+  rB0 = (__float_as_uint(aH.x) | __float_as_uint(bH.x) | __float_as_uint(eH.x)) & __float_as_uint(fH.x);
+  rB1 = (__float_as_uint(aH.y) | __float_as_uint(bH.y) | __float_as_uint(eH.y)) & __float_as_uint(fH.y);
+}
+
+// The fan flags of the (up to) 16 groups of a 64-triangle chunk, bit 0 = its first group.
+__device__ __forceinline__ uint32_t fanBitsOfChunk(const uint32_t *__restrict__ fanMask, uint32_t firstGroup) {
+  const uint32_t word = firstGroup >> 5, shift = firstGroup & 31u;
+  const uint32_t lo = __ldg(fanMask + word), hi = __ldg(fanMask + word + 1); // (one spare word is allocated)
+  return __funnelshift_r(lo, hi, shift);
+}
+
 // Sweeps a staged tile of moment-form data; same survivor bookkeeping as sweepTileStage0Signs().
 template <bool kFpWay = false>
 __device__ __forceinline__ void sweepTileStage0Moment(const float *__restrict__ filter,
                                                       const double *__restrict__ exact, int count,
-                                                      int firstIndex, V3 o, V3 d, Nearest &best) {
+                                                      int firstIndex, V3 o, V3 d, Nearest &best,
+                                                      const uint32_t *__restrict__ fanMask) {
   const MomentRay r = makeMomentRay(o, d);
 #pragma unroll 1
   for (int chunk = 0; chunk < count; chunk += 64) {
     const int chunkEnd = min(count, chunk + 64);
+    uint32_t fanBits = fanBitsOfChunk(fanMask, static_cast<uint32_t>(firstIndex + chunk) >> 2);
     uint32_t rejectedHi = 0xffffffffu, rejectedLo = 0xffffffffu;
     const float4 *group = reinterpret_cast<const float4 *>(filter) + (chunk >> 2) * kMomentFloats;
     const float4 *const groupEnd = reinterpret_cast<const float4 *>(filter) + (chunkEnd >> 2) * kMomentFloats;
@@ -606,8 +666,12 @@ __device__ __forceinline__ void sweepTileStage0Moment(const float *__restrict__ 
 #pragma unroll
       for (int k = 0; k < kMomentFloats; ++k)
         a[k] = group[k];
-      uint32_t r0, r1, r2bits, r3;
-      stage0RejectMoment4(a, r, r0, r1, r2bits, r3);
+      uint32_t r0, r1, r2bits, r3; // in triangle-index order
+      if (fanBits & 1u) // warp-uniform; lanes [A0, A1, B0, B1] = triangles 4g + {0, 2, 1, 3}
+        stage0RejectFan4(a, r, r0, r2bits, r1, r3);
+      else
+        stage0RejectMoment4(a, r, r0, r1, r2bits, r3);
+      fanBits >>= 1;
       rejectedHi = __funnelshift_l(rejectedLo, rejectedHi, 4);
       rejectedLo = __funnelshift_l(r0, rejectedLo, 1);
       rejectedLo = __funnelshift_l(r1, rejectedLo, 1);
@@ -693,36 +757,57 @@ __device__ __forceinline__ void survivorsOfChunk(unsigned long long keep, const 
 }
 __device__ __forceinline__ void sweepTileStage0Moment2(const float *__restrict__ filter, const double *__restrict__ exact,
                                                        int count, int firstIndex, V3 o0, V3 d0, bool live0, Nearest &best0,
-                                                       V3 o1, V3 d1, bool live1, Nearest &best1) {
+                                                       V3 o1, V3 d1, bool live1, Nearest &best1,
+                                                       const uint32_t *__restrict__ fanMask) {
   const MomentRay ray0 = makeMomentRay(o0, d0), ray1 = makeMomentRay(o1, d1);
 #pragma unroll 1
   for (int chunk = 0; chunk < count; chunk += 64) {
     const int chunkEnd = min(count, chunk + 64);
+    uint32_t fanBits = fanBitsOfChunk(fanMask, static_cast<uint32_t>(firstIndex + chunk) >> 2);
     uint32_t hi0 = 0xffffffffu, lo0 = 0xffffffffu, hi1 = 0xffffffffu, lo1 = 0xffffffffu;
     const float4 *group = reinterpret_cast<const float4 *>(filter) + (chunk >> 2) * kMomentFloats;
     const float4 *const groupEnd = reinterpret_cast<const float4 *>(filter) + (chunkEnd >> 2) * kMomentFloats;
 #pragma unroll 1
     for (; group != groupEnd; group += kMomentFloats) {
+      const bool fan = (fanBits & 1u) != 0; // warp-uniform: lanes [A0, A1, B0, B1], Y of the B pair = -X of the A pair
+      fanBits >>= 1;
       Stage0Sums sums0, sums1;
 #pragma unroll
-      for (int k = 0; k < 15; ++k) {
+      for (int k = 0; k < 9; ++k) {
         const float4 a = group[k];
         stage0Accumulate(sums0, ray0, k, a);
         stage0Accumulate(sums1, ray1, k, a);
       }
+      if (fan) {
+#pragma unroll
+        for (int k = 9; k < 15; ++k) {
+          const float2 lo = *reinterpret_cast<const float2 *>(group + k);
+          stage0Accumulate(sums0, ray0, k, make_float4(lo.x, lo.y, 0.f, 0.f));
+          stage0Accumulate(sums1, ray1, k, make_float4(lo.x, lo.y, 0.f, 0.f));
+        }
+        sums0.yH = neg2(sums0.xL);
+        sums1.yH = neg2(sums1.xL);
+      } else {
+#pragma unroll
+        for (int k = 9; k < 15; ++k) {
+          const float4 a = group[k];
+          stage0Accumulate(sums0, ray0, k, a);
+          stage0Accumulate(sums1, ray1, k, a);
+        }
+      }
       const float4 ed = group[15], kx = group[16], ky = group[17], k3 = group[18];
-      uint32_t r0, r1, r2, r3;
+      uint32_t r0, r1, r2, r3; // lane order; a fan group's triangle-index order is r0, r2, r1, r3
       stage0Decide(sums0, ray0, ed, kx, ky, k3, r0, r1, r2, r3);
       hi0 = __funnelshift_l(lo0, hi0, 4);
       lo0 = __funnelshift_l(r0, lo0, 1);
-      lo0 = __funnelshift_l(r1, lo0, 1);
-      lo0 = __funnelshift_l(r2, lo0, 1);
+      lo0 = __funnelshift_l(fan ? r2 : r1, lo0, 1);
+      lo0 = __funnelshift_l(fan ? r1 : r2, lo0, 1);
       lo0 = __funnelshift_l(r3, lo0, 1);
       stage0Decide(sums1, ray1, ed, kx, ky, k3, r0, r1, r2, r3);
       hi1 = __funnelshift_l(lo1, hi1, 4);
       lo1 = __funnelshift_l(r0, lo1, 1);
-      lo1 = __funnelshift_l(r1, lo1, 1);
-      lo1 = __funnelshift_l(r2, lo1, 1);
+      lo1 = __funnelshift_l(fan ? r2 : r1, lo1, 1);
+      lo1 = __funnelshift_l(fan ? r1 : r2, lo1, 1);
       lo1 = __funnelshift_l(r3, lo1, 1);
     }
     // left-align: triangle chunk + k at bit 63 - k; the slots past chunkEnd read "rejected"
@@ -749,54 +834,6 @@ struct MomentTable {
   uint32_t fanGroups; // bit g: group g holds two FAN PAIRS, lanes ordered [A0, A1, B0, B1] (see below)
 };
 
-// A quad face `f a b c d` reaches the scene as the fan (a,b,c), (a,c,d) (ObjLoaderImpl.h:75-85): triangle
-// B shares v0 with triangle A and its first edge IS A's second edge, bit for bit.  Then B's
-// Y numerator is A's X numerator negated —  Y_B = -e1_B.m - d.(v0 x e1_B) = -(e2_A.m + d.(v0 x e2_A))
-// = -X_A  — through the very same operations (negation commutes with rounding), so a group of two
-// such quads, packed as [A0, A1 | B0, B1], needs Y for its first pair only: 24 instead of 30 packed
-// operations and 32 instead of 38 constant loads per four triangles, the same decisions bit for bit.
-// The upload marks the groups that qualify (exact comparisons of the stored doubles).
-__device__ __forceinline__ void stage0RejectFan4(const float4 (&a)[kMomentFloats], const MomentRay &r,
-                                                 uint32_t &rA0, uint32_t &rA1, uint32_t &rB0, uint32_t &rB1) {
-#define PT_LO(k) make_float2(a[k].x, a[k].y)
-#define PT_HI(k) make_float2(a[k].z, a[k].w)
-  float2 detL = __fmul2_rn(splat(r.dx), PT_LO(0)), detH = __fmul2_rn(splat(r.dx), PT_HI(0));
-  detL = __ffma2_rn(splat(r.dy), PT_LO(1), detL), detH = __ffma2_rn(splat(r.dy), PT_HI(1), detH);
-  detL = __ffma2_rn(splat(r.dz), PT_LO(2), detL), detH = __ffma2_rn(splat(r.dz), PT_HI(2), detH);
-  float2 xL = __fmul2_rn(splat(r.mx), PT_LO(3)), xH = __fmul2_rn(splat(r.mx), PT_HI(3));
-  xL = __ffma2_rn(splat(r.my), PT_LO(4), xL), xH = __ffma2_rn(splat(r.my), PT_HI(4), xH);
-  xL = __ffma2_rn(splat(r.mz), PT_LO(5), xL), xH = __ffma2_rn(splat(r.mz), PT_HI(5), xH);
-  xL = __ffma2_rn(splat(r.dx), PT_LO(6), xL), xH = __ffma2_rn(splat(r.dx), PT_HI(6), xH);
-  xL = __ffma2_rn(splat(r.dy), PT_LO(7), xL), xH = __ffma2_rn(splat(r.dy), PT_HI(7), xH);
-  xL = __ffma2_rn(splat(r.dz), PT_LO(8), xL), xH = __ffma2_rn(splat(r.dz), PT_HI(8), xH);
-  float2 yL = __fmul2_rn(splat(r.mx), PT_LO(9));
-  yL = __ffma2_rn(splat(r.my), PT_LO(10), yL);
-  yL = __ffma2_rn(splat(r.mz), PT_LO(11), yL);
-  yL = __ffma2_rn(splat(r.dx), PT_LO(12), yL);
-  yL = __ffma2_rn(splat(r.dy), PT_LO(13), yL);
-  yL = __ffma2_rn(splat(r.dz), PT_LO(14), yL);
-  const float2 yH = neg2(xL); // the fan identity
-  uint32_t s0, s1, s2, s3; // copysign(1, det)
-  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s0) : "r"(__float_as_uint(detL.x)), "r"(r.one));
-  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s1) : "r"(__float_as_uint(detL.y)), "r"(r.one));
-  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s2) : "r"(__float_as_uint(detH.x)), "r"(r.one));
-  asm("lop3.b32 %0, %1, 0x80000000, %2, 0xEA;" : "=r"(s3) : "r"(__float_as_uint(detH.y)), "r"(r.one));
-  const float2 sL = make_float2(__uint_as_float(s0), __uint_as_float(s1));
-  const float2 sH = make_float2(__uint_as_float(s2), __uint_as_float(s3));
-  const float2 adetL = make_float2(fabsf(detL.x), fabsf(detL.y)), adetH = make_float2(fabsf(detH.x), fabsf(detH.y));
-  const float2 fL = __fadd2_rn(PT_LO(15), neg2(adetL)), fH = __fadd2_rn(PT_HI(15), neg2(adetH));
-  const float2 aL = __ffma2_rn(xL, sL, PT_LO(16)), aH = __ffma2_rn(xH, sH, PT_HI(16));
-  const float2 bL = __ffma2_rn(yL, sL, PT_LO(17)), bH = __ffma2_rn(yH, sH, PT_HI(17));
-  const float2 boundL = __ffma2_rn(adetL, splat(1.0f + 0x1p-20f), PT_LO(18));
-  const float2 boundH = __ffma2_rn(adetH, splat(1.0f + 0x1p-20f), PT_HI(18));
-  const float2 eL = __ffma2_rn(neg2(__fadd2_rn(xL, yL)), sL, boundL), eH = __ffma2_rn(neg2(__fadd2_rn(xH, yH)), sH, boundH);
-#undef PT_LO
-#undef PT_HI
-  rA0 = (__float_as_uint(aL.x) | __float_as_uint(bL.x) | __float_as_uint(eL.x)) & __float_as_uint(fL.x);
-  rA1 = (__float_as_uint(aL.y) | __float_as_uint(bL.y) | __float_as_uint(eL.y)) & __float_as_uint(fL.y);
-  rB0 = (__float_as_uint(aH.x) | __float_as_uint(bH.x) | __float_as_uint(eH.x)) & __float_as_uint(fH.x);
-  rB1 = (__float_as_uint(aH.y) | __float_as_uint(bH.y) | __float_as_uint(eH.y)) & __float_as_uint(fH.y);
-}
 // `exact`: the AoS FP64 records of the survivors' test (triExact layout), here in SHARED memory —
 // the gather of 80-byte records was the other big client of the L1 data pipe.
 template <bool kFpWay = false, bool kUnrolled = true>

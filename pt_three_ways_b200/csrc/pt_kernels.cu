@@ -879,8 +879,10 @@ __global__ void buildFilterKernel(const __grid_constant__ BuildFilterArgs args) 
   dst[13 * 4] = fkt;
   // Moment (Pluecker) form for sweep variant 7, blocked [tile][group of 4][19][4]: the per-triangle
   // constants of stage0RejectMoment(), evaluated in FP64 and rounded once; the same bounds.
-  float *mom = args.outMoment + (static_cast<size_t>(tile) * (scene.tileTris / 4) + within / 4) * (kMomentFloats * 4) +
-               within % 4;
+  const uint32_t groupIndex = tile * (scene.tileTris / 4) + within / 4;
+  const bool fan = (scene.fanMask[groupIndex >> 5] >> (groupIndex & 31u)) & 1u;
+  const uint32_t lanePosition = fan ? ((within & 1u) << 1 | ((within >> 1) & 1u)) : within % 4; // [A0, A1, B0, B1]
+  float *mom = args.outMoment + static_cast<size_t>(groupIndex) * (kMomentFloats * 4) + lanePosition;
   const V3 v0 = mk(v[0], v[1], v[2]), e1 = mk(v[3], v[4], v[5]), e2 = mk(v[6], v[7], v[8]);
   const V3 nn = cross(e2, e1), a2 = cross(v0, e2), a1 = cross(v0, e1);
   const double moment[15] = {nn.x, nn.y, nn.z, e2.x, e2.y, e2.z, a2.x, a2.y, a2.z,
@@ -911,8 +913,12 @@ __global__ void auditStage0Kernel(const __grid_constant__ AuditArgs args) {
                        (static_cast<size_t>(tile) * (scene.tileTris / 4) + i / 4) * (kFilterFloats * 4) + i % 4;
       const double *e = scene.triSweep + static_cast<size_t>(tile) * 9 * scene.tileTris + i;
       const uint32_t n = scene.tileTris;
-      const float *g = scene.triMoment +
-                       (static_cast<size_t>(tile) * (scene.tileTris / 4) + i / 4) * (kMomentFloats * 4) + i % 4;
+      const uint32_t groupIndex = tile * (scene.tileTris / 4) + i / 4;
+      const bool fan = (scene.fanMask[groupIndex >> 5] >> (groupIndex & 31u)) & 1u;
+      // (a fan group's second triangles keep their own Y rows: the audit checks the plain decision,
+      // which the fan identity reproduces bit for bit)
+      const float *g = scene.triMoment + static_cast<size_t>(groupIndex) * (kMomentFloats * 4) +
+                       (fan ? ((i & 1u) << 1 | ((i >> 1) & 1u)) : i % 4);
       const bool keep = args.momentForm
                             ? stage0KeepMoment(g, 4, momentRay)
                             : stage0Keep(f[0], f[4], f[8], f[12], f[16], f[20], f[24], f[28], f[32], f[36], f[40], f[44],

@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kBlock, 1) subPathDualKernel(const __grid_cons
       const int first = static_cast<int>(j * scene.tileTris);
       sweepTileStage0Moment2(reinterpret_cast<const float *>(tile), scene.triExact + static_cast<size_t>(first) * 10,
                              static_cast<int>(scene.tileTris), first, path0.origin, path0.direction, tracing0, best0,
-                             path1.origin, path1.direction, tracing1, best1);
+                             path1.origin, path1.direction, tracing1, best1, scene.fanMask);
       if (!resident)
         stream.release();
     }

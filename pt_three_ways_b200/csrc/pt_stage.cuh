@@ -108,7 +108,7 @@ __device__ __forceinline__ void sweepStagedTile(const DeviceScene &scene, const 
   const int first = static_cast<int>(tileIndex * scene.tileTris);
   if (kSweep == 7)
     sweepTileStage0Moment<kFpWay>(reinterpret_cast<const float *>(tile), scene.triExact + static_cast<size_t>(first) * 10,
-                                  tileTris, first, o, d, best);
+                                  tileTris, first, o, d, best, scene.fanMask);
   else if (kSweep >= 5)
     sweepTileStage0Signs<kSweep == 5, kFpWay>(reinterpret_cast<const float *>(tile),
                     scene.triExact + static_cast<size_t>(first) * 10, tileTris, first, o, d, best);

@@ -148,6 +148,7 @@ struct PtContext {
   DeviceBuffer<double> materials;
   DeviceBuffer<float> triFilter;
   DeviceBuffer<float> triMoment;
+  DeviceBuffer<uint32_t> fanMask;
   MomentTable momentHost{};    // host copy of triMoment for scenes whose table rides in the kernel parameters
   bool momentHostValid{false};
   uint32_t fanGroups{0};       // groups of four triangles that are two quads in fan order (pt_device.cuh)
@@ -402,21 +403,23 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
       longestEdge = std::max(longestEdge, std::sqrt(ex * ex + ey * ey + ez * ez));
     }
   }
-  // Groups of four consecutive triangles that are two quads in fan order: (v0, e1, e2), (v0, e2, e3)
-  // twice, compared as stored doubles (all-zero padding qualifies too).
-  ctx->fanGroups = 0;
-  if (d.numTiles == 1 && d.tileTris <= 4u * kConstGroups) {
-    auto value = [&](uint32_t tri, int k) { return tri < scene->numTriangles ? exact[10 * static_cast<size_t>(tri) + k] : 0.0; };
+  // Groups of four consecutive triangles (of a tile) that are two quads in fan order: (v0, e1, e2),
+  // (v0, e2, e3) twice, compared as stored doubles (all-zero padding qualifies too).
+  const uint32_t numGroups = d.numTiles * (d.tileTris / 4);
+  std::vector<uint32_t> fanMask(numGroups / 32 + 2, 0u);
+  if (!std::getenv("PTB200_NO_FAN_GROUPS")) {
+    auto value = [&](uint32_t slot, int k) { return exact[10 * static_cast<size_t>(slot) + k]; };
     auto fanPair = [&](uint32_t a, uint32_t b) {
       for (int k = 0; k < 3; ++k)
         if (value(a, k) != value(b, k) || value(a, 6 + k) != value(b, 3 + k)) // same v0; e2 of A == e1 of B
           return false;
       return true;
     };
-    for (uint32_t g = 0; g * 4 < d.tileTris; ++g)
+    for (uint32_t g = 0; g < numGroups; ++g)
       if (fanPair(4 * g, 4 * g + 1) && fanPair(4 * g + 2, 4 * g + 3))
-        ctx->fanGroups |= 1u << g;
+        fanMask[g >> 5] |= 1u << (g & 31u);
   }
+  ctx->fanGroups = fanMask[0] & 0xffffu;
   ctx->sceneRadius = radius;
   ctx->filterUsable = std::isfinite(radius) && radius < 1e6 && longestEdge < 1e6;
   ctx->filterOriginBound = -1;
@@ -426,6 +429,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   PT_CUDA(ctx->triShade.ensure(shade.size()));
   PT_CUDA(ctx->triFilter.ensure(static_cast<size_t>(d.numTiles) * 14 * d.tileTris));
   PT_CUDA(ctx->triMoment.ensure(static_cast<size_t>(d.numTiles) * 19 * d.tileTris));
+  PT_CUDA(ctx->fanMask.ensure(fanMask.size()));
   PT_CUDA(ctx->triExact.ensure(exact.size()));
   PT_CUDA(ctx->spheres.ensure(spheres.size()));
   PT_CUDA(ctx->sphereMaterial.ensure(scene->numSpheres));
@@ -439,6 +443,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
     PT_CUDA(cudaMemcpyAsync(ctx->triSweep.ptr, sweep.data(), sweepDoubles * 8, cudaMemcpyHostToDevice, ctx->stream));
     PT_CUDA(cudaMemcpyAsync(ctx->triExact.ptr, exact.data(), exact.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
   }
+  PT_CUDA(cudaMemcpyAsync(ctx->fanMask.ptr, fanMask.data(), fanMask.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
   if (!shade.empty())
     PT_CUDA(cudaMemcpyAsync(ctx->triShade.ptr, shade.data(), shade.size() * 32, cudaMemcpyHostToDevice, ctx->stream));
   if (!spheres.empty()) {
@@ -455,6 +460,7 @@ int ptb200_context_upload_scene(PtContext *ctx, const PtScene *scene) {
   d.materials = ctx->materials.ptr;
   d.triFilter = ctx->triFilter.ptr;
   d.triMoment = ctx->triMoment.ptr;
+  d.fanMask = ctx->fanMask.ptr;
   d.triExact = ctx->triExact.ptr;
   d.environment[0] = scene->environment[0];
   d.environment[1] = scene->environment[1];
@@ -482,13 +488,7 @@ static int ensureFilter(PtContext *ctx, double originBound, uint64_t *launches) 
     PT_CUDA(cudaMemcpyAsync(&ctx->momentHost, ctx->triMoment.ptr, static_cast<size_t>(ctx->scene.tileTris) * 19 * sizeof(float),
                             cudaMemcpyDeviceToHost, ctx->stream));
     PT_CUDA(cudaStreamSynchronize(ctx->stream));
-    // Fan groups carry their lanes as [A0, A1, B0, B1]: swap the two middle triangles of every row.
-    const uint32_t usable = std::getenv("PTB200_NO_FAN_GROUPS") ? 0u : ctx->fanGroups;
-    for (int g = 0; g < kConstGroups; ++g)
-      if (usable & (1u << g))
-        for (float4 &row : ctx->momentHost.group[g])
-          std::swap(row.y, row.z);
-    ctx->momentHost.fanGroups = usable;
+    ctx->momentHost.fanGroups = ctx->fanGroups; // (buildFilterKernel already stored those groups as [A0, A1, B0, B1])
     ctx->momentHostValid = true;
   }
   if (launches && ctx->scene.numTiles)
