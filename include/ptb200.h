@@ -115,7 +115,9 @@ typedef struct PtRenderOptions {
   int32_t rowBegin;       /* framebuffer partition: this call renders rows y with          */
   int32_t rowStep;        /*   y >= rowBegin and (y-rowBegin) % rowStep == 0; 0 means 1     */
   int32_t passesPerBatch; /* 0 = library default; progress callback runs between batches   */
-  int32_t reserved[2];
+  int32_t lanesPerPass;   /* sequential policies: lanes that share one pass (4, 8, 16 or 32);    */
+                          /*   0 = chosen from the number of passes                           */
+  int32_t reserved[1];
 } PtRenderOptions;
 
 /* SampledPixel (src/util/SampledPixel.h:5-7): sum of colours and the sample count. */

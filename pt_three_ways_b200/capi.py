@@ -57,7 +57,7 @@ class PtRenderParams(C.Structure):
 class PtRenderOptions(C.Structure):
     _fields_ = [("rngMode", C.c_int32), ("device", C.c_int32), ("passBegin", C.c_int32),
                 ("rowBegin", C.c_int32), ("rowStep", C.c_int32), ("passesPerBatch", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("lanesPerPass", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class PtStats(C.Structure):
@@ -168,8 +168,8 @@ def make_params(width, height, spp=1, seed=1, max_depth=5, first_u=4, first_v=4,
 
 
 def make_options(rng_mode=RNG_KEYED_PHILOX, device=0, pass_begin=0, row_begin=0, row_step=0,
-                 passes_per_batch=0) -> PtRenderOptions:
-    return PtRenderOptions(rng_mode, device, pass_begin, row_begin, row_step, passes_per_batch)
+                 passes_per_batch=0, lanes_per_pass=0) -> PtRenderOptions:
+    return PtRenderOptions(rng_mode, device, pass_begin, row_begin, row_step, passes_per_batch, lanes_per_pass)
 
 
 def _stats_dict(st: PtStats) -> dict:

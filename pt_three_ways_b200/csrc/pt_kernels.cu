@@ -410,14 +410,25 @@ __global__ void __launch_bounds__(kBlock, kMinBlocks)
 }
 
 // =============================================================================================
-// Sequential (mt19937) kernel: one pass per warp, the reference's exact stream.
+// Sequential (mt19937) kernel: the reference's exact stream, one pass per GROUP of kGroup lanes
+// (a whole warp, or 16 / 8 / 4 lanes so that a warp walks 2 / 4 / 8 passes side by side).
 // =============================================================================================
-struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instance per warp
-  uint32_t *state; // 624 words
-  int index;       // warp-uniform
+template <int kGroup>
+__device__ __forceinline__ unsigned groupMaskOf(unsigned lane) {
+  return kGroup == 32 ? kFullMask : ((1u << (kGroup & 31)) - 1u) << (lane & ~static_cast<unsigned>(kGroup - 1));
+}
 
-  __device__ __forceinline__ void seed(uint32_t value, unsigned lane) {
-    if (lane == 0) {
+// std::mt19937 with its state in shared memory, one instance per pass; `index` is uniform over
+// the group's lanes.
+template <int kGroup>
+struct GroupMt19937 {
+  uint32_t *state; // 624 words
+  int index;
+  unsigned mask;   // the lanes of this group
+  unsigned glane;  // lane within the group
+
+  __device__ __forceinline__ void seed(uint32_t value) {
+    if (glane == 0) {
       uint32_t x = value;
       state[0] = x;
       for (int i = 1; i < 624; ++i) {
@@ -426,40 +437,25 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
       }
     }
     index = 624;
-    __syncwarp();
+    __syncwarp(mask);
   }
-  // The twist, 32 words at a time in index order; loads precede stores within a batch, so
+  // The twist, kGroup words at a time in index order; loads precede stores within a batch, so
   // word i sees old[i], old[i+1] and (i < 227 ? old : new)[i+397 mod 624] as the serial
-  // algorithm does.
-  __device__ __noinline__ void refill(unsigned lane) {
-    for (int batch = 0; batch < 640; batch += 32) {
-      const int i = batch + static_cast<int>(lane);
+  // algorithm does (a batch is at most 32 < 227 words).
+  __device__ __noinline__ void refill() {
+    for (int batch = 0; batch < 624; batch += kGroup) {
+      const int i = batch + static_cast<int>(glane);
       uint32_t value = 0;
       if (i < 624) {
         const uint32_t y = (state[i] & 0x80000000u) | (state[(i + 1) % 624] & 0x7fffffffu);
         value = state[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
       }
-      __syncwarp();
+      __syncwarp(mask);
       if (i < 624)
         state[i] = value;
-      __syncwarp();
+      __syncwarp(mask);
     }
     index = 0;
-  }
-  __device__ __forceinline__ uint32_t next(unsigned lane) {
-    if (index >= 624)
-      refill(lane);
-    uint32_t y = state[index++];
-    y ^= y >> 11;
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= y >> 18;
-    return y;
-  }
-  __device__ __forceinline__ double canonical(unsigned lane) {
-    const uint32_t lo = next(lane);
-    const uint32_t hi = next(lane);
-    return canonicalFromWords(lo, hi);
   }
   __device__ __forceinline__ static uint32_t temper(uint32_t y) {
     y ^= y >> 11;
@@ -468,9 +464,31 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
     y ^= y >> 18;
     return y;
   }
-  // Three canonical doubles (six outputs) at once: when they do not straddle a refill the six
-  // state words are read independently instead of through six dependent next() calls.
-  __device__ __forceinline__ void canonical3(unsigned lane, double &a, double &b, double &c) {
+  __device__ __forceinline__ uint32_t next() {
+    if (index >= 624)
+      refill();
+    return temper(state[index++]);
+  }
+  __device__ __forceinline__ double canonical() {
+    const uint32_t lo = next();
+    const uint32_t hi = next();
+    return canonicalFromWords(lo, hi);
+  }
+  // Two / three canonical doubles at once: when they do not straddle a refill the state words are
+  // read independently instead of through dependent next() calls.
+  __device__ __forceinline__ void canonical2(double &a, double &b) {
+    if (index + 4 <= 624) {
+      const uint32_t w0 = temper(state[index]), w1 = temper(state[index + 1]), w2 = temper(state[index + 2]),
+                     w3 = temper(state[index + 3]);
+      index += 4;
+      a = canonicalFromWords(w0, w1);
+      b = canonicalFromWords(w2, w3);
+    } else {
+      a = canonical();
+      b = canonical();
+    }
+  }
+  __device__ __forceinline__ void canonical3(double &a, double &b, double &c) {
     if (index + 6 <= 624) {
       const uint32_t w0 = temper(state[index]), w1 = temper(state[index + 1]), w2 = temper(state[index + 2]),
                      w3 = temper(state[index + 3]), w4 = temper(state[index + 4]), w5 = temper(state[index + 5]);
@@ -479,16 +497,16 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
       b = canonicalFromWords(w2, w3);
       c = canonicalFromWords(w4, w5);
     } else {
-      a = canonical(lane);
-      b = canonical(lane);
-      c = canonical(lane);
+      a = canonical();
+      b = canonical();
+      c = canonical();
     }
   }
   // Discards `count` outputs.
-  __device__ __forceinline__ void skip(uint32_t count, unsigned lane) {
+  __device__ __forceinline__ void skip(uint32_t count) {
     while (count) {
       if (index >= 624)
-        refill(lane);
+        refill();
       const uint32_t step = min(count, static_cast<uint32_t>(624 - index));
       index += static_cast<int>(step);
       count -= step;
@@ -496,16 +514,15 @@ struct WarpMt19937 { // std::mt19937 with its state in shared memory, one instan
   }
 };
 
-// Whole-warp Scene::intersect: lanes stride the primitive lists, then an argmin.
-// kAcceptEpsilon: oo::Triangle::intersect (src/oo/Triangle.cpp:31) rejects `t < Epsilon` where
-// Scene.cpp:94 accepts `t > Epsilon`.
-template <bool kAcceptEpsilon = false>
-__device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o, V3 d, unsigned lane,
-                                                 bool useSpheres, bool useTriangles,
-                                                 double nearerThanLimit) {
+// Scene::intersect by a group of kGroup lanes: the lanes stride the primitive lists, then an argmin
+// over the group.  kAcceptEpsilon: oo::Triangle::intersect (src/oo/Triangle.cpp:31) rejects
+// `t < Epsilon` where Scene.cpp:94 accepts `t > Epsilon`.
+template <int kGroup, bool kAcceptEpsilon = false>
+__device__ __forceinline__ Nearest groupIntersect(const DeviceScene &scene, V3 o, V3 d, unsigned glane, unsigned mask,
+                                                  bool useSpheres, bool useTriangles, double nearerThanLimit) {
   Nearest best{nearerThanLimit, 0.0, kNoPrim};
   if (useSpheres) {
-    for (uint32_t i = lane; i < scene.numSpheres; i += 32) {
+    for (uint32_t i = glane; i < scene.numSpheres; i += kGroup) {
       const double4 s = ldgDouble4(scene.spheres + i); // loop body of Scene.cpp:17-36
       const V3 op = sub(mk(s.x, s.y, s.z), o);
       const double b = dot(op, d);
@@ -531,7 +548,7 @@ __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o,
     // and reject themselves.  (Unrolling this loop by two was measured: 10 % slower.)
     const uint32_t slots = scene.numTiles * scene.tileTris;
 #pragma unroll 1
-    for (uint32_t index = lane; index < slots; index += 32) {
+    for (uint32_t index = glane; index < slots; index += kGroup) {
       const double2 *record = reinterpret_cast<const double2 *>(scene.triExact + 10 * static_cast<size_t>(index));
       const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
                     a4 = __ldg(record + 4);
@@ -539,40 +556,60 @@ __device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o,
                                    static_cast<int>(index), best);
     }
   }
-  // Warp argmin in the serial scans' order (t, sphere-before-triangle, index) with three
+  // Group argmin in the serial scans' order (t, sphere-before-triangle, index) with three
   // integer min-reductions: hit distances are positive, so their bit patterns order like
   // unsigned integers.
   const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(best.t));
   const uint32_t hi = static_cast<uint32_t>(bits >> 32), lo = static_cast<uint32_t>(bits);
-  const uint32_t minHi = __reduce_min_sync(kFullMask, hi);
-  const uint32_t minLo = __reduce_min_sync(kFullMask, hi == minHi ? lo : 0xffffffffu);
+  const uint32_t minHi = __reduce_min_sync(mask, hi);
+  const uint32_t minLo = __reduce_min_sync(mask, hi == minHi ? lo : 0xffffffffu);
   const bool nearest = hi == minHi && lo == minLo;
   const uint32_t order = best.prim == kNoPrim ? 0xffffffffu
                          : best.prim < 0      ? static_cast<uint32_t>(-best.prim - 1)
                                               : 0x40000000u + static_cast<uint32_t>(best.prim);
-  const uint32_t minOrder = __reduce_min_sync(kFullMask, nearest ? order : 0xffffffffu);
-  const int winner = __ffs(__ballot_sync(kFullMask, nearest && order == minOrder)) - 1;
-  best.t = __shfl_sync(kFullMask, best.t, winner);
-  best.det = __shfl_sync(kFullMask, best.det, winner);
-  best.prim = __shfl_sync(kFullMask, best.prim, winner);
+  const uint32_t minOrder = __reduce_min_sync(mask, nearest ? order : 0xffffffffu);
+  const int winner = __ffs(__ballot_sync(mask, nearest && order == minOrder)) - 1; // a lane of the warp
+  best.t = __shfl_sync(mask, best.t, winner);
+  best.det = __shfl_sync(mask, best.det, winner);
+  best.prim = __shfl_sync(mask, best.prim, winner);
   return best;
 }
 
+template <bool kAcceptEpsilon = false>
+__device__ __forceinline__ Nearest warpIntersect(const DeviceScene &scene, V3 o, V3 d, unsigned lane,
+                                                 bool useSpheres, bool useTriangles,
+                                                 double nearerThanLimit) {
+  return groupIntersect<32, kAcceptEpsilon>(scene, o, d, lane, kFullMask, useSpheres, useTriangles, nearerThanLimit);
+}
+
+// One pass = one std::mt19937(seed + s) walked over the frame in row-major order, camera ray then
+// radiance() per pixel (Scene.cpp:208-216): the work within a pass is one dependent chain, so the only
+// parallelism is passes x primitives.  A group's lanes share the pass: they split the primitive
+// list in groupIntersect() and compute everything else redundantly (group-uniform); the groups of a
+// warp run the same state machine on different passes and diverge like the keyed kernel's lanes do.
+// Smaller groups mean less redundant shading per pass and more sweep trips per cast: the launcher
+// picks the group from the number of passes (sequentialLanesPerPass()).
+//
 // kOo: the reference's `oo` way (src/oo/Renderer.cpp:60-107) walks the same stream in the same
 // order; its estimator differs from Scene::radiance in where the emission is added
 // (Material::totalEmission after the average, :90) and in accepting t == Epsilon.
-template <int kWarps, bool kOo>
+template <int kWarps, int kGroup, bool kOo>
 __global__ void __launch_bounds__(kWarps * 32)
     renderSequentialKernel(const __grid_constant__ SequentialArgs args) {
-  __shared__ uint32_t mtState[kWarps][624];
+  constexpr int kPassesPerWarp = 32 / kGroup;
+  __shared__ uint32_t mtState[kWarps * kPassesPerWarp][624];
   const DeviceScene &scene = args.scene;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
-  const int passInBatch = static_cast<int>(blockIdx.x) * kWarps + static_cast<int>(warp);
+  const unsigned glane = lane & static_cast<unsigned>(kGroup - 1);
+  const unsigned groupInWarp = lane / kGroup;
+  const unsigned mask = groupMaskOf<kGroup>(lane);
+  const int passInBatch = (static_cast<int>(blockIdx.x) * kWarps + static_cast<int>(warp)) * kPassesPerWarp +
+                          static_cast<int>(groupInWarp);
   if (passInBatch >= args.numPasses)
     return;
-  WarpMt19937 rng{mtState[warp], 624};
-  rng.seed(static_cast<uint32_t>(args.seed + args.passBegin + passInBatch), lane);
+  GroupMt19937<kGroup> rng{mtState[warp * kPassesPerWarp + groupInWarp], 624, mask, glane};
+  rng.seed(static_cast<uint32_t>(args.seed + args.passBegin + passInBatch));
 
   const int numSub = args.firstBounceU * args.firstBounceV;
   const double invNumSub = 1.0 / static_cast<double>(numSub);
@@ -583,137 +620,145 @@ __global__ void __launch_bounds__(kWarps * 32)
   uint16_t stackMaterial[kMaxDepth];
   bool stackSpecular[kMaxDepth];
 
-  // Everything below is warp-uniform: the 32 lanes only differ inside warpIntersect().
+  // Everything below is uniform over the group: its lanes only differ inside groupIntersect().
   const int numPixels = args.width * args.height;
-  for (int pixelIndex = 0; pixelIndex < numPixels; ++pixelIndex) { // row-major (Scene.cpp:212-213)
-    const int px = pixelIndex % args.width;
-    const int py = pixelIndex / args.width;
-    // Camera::randomRay draws before radiance() looks at the depth (Scene.cpp:214-215).
-    const double ux = rng.canonical(lane);
-    const double uy = rng.canonical(lane);
-    double ua = 0, ur = 0;
-    if (args.camera.apertureRadius != 0) {
-      ua = rng.canonical(lane);
-      ur = rng.canonical(lane);
+  int pixelIndex = -1;
+  int px = -1, py = 0;
+  V3 origin = mk(0, 0, 0), direction = mk(0, 0, 1);
+  V3 colour = mk(0, 0, 0);
+  int depth = 0;
+  int subPath = 0;
+  Surface primary{};
+  bool primarySpecular = false;
+  V3 acc = mk(0, 0, 0);
+  bool sampleDone = true;
+
+  for (;;) { // the keyed megakernel's state machine, one path at a time per group
+    if (sampleDone) { // store the finished pixel, start the next one: row-major (Scene.cpp:212-213)
+      if (pixelIndex >= 0 && glane == 0) {
+        double *dst = passSamples + 3 * static_cast<size_t>(pixelIndex);
+        dst[0] = colour.x;
+        dst[1] = colour.y;
+        dst[2] = colour.z;
+      }
+      if (++pixelIndex >= numPixels)
+        break;
+      if (++px == args.width) {
+        px = 0;
+        ++py;
+      }
+      // Camera::randomRay draws before radiance() looks at the depth (Scene.cpp:214-215).
+      double ux, uy, ua = 0, ur = 0;
+      rng.canonical2(ux, uy);
+      if (args.camera.apertureRadius != 0)
+        rng.canonical2(ua, ur);
+      cameraRay(args.camera, px, py, ux, uy, ua, ur, origin, direction);
+      colour = mk(0, 0, 0);
+      depth = 0;
+      subPath = 0;
+      sampleDone = args.maxDepth <= 0; // radiance() returns Vec3() at once (Scene.cpp:128-129)
+      if (sampleDone)
+        continue;
     }
-    V3 origin, direction;
-    cameraRay(args.camera, px, py, ux, uy, ua, ur, origin, direction);
-
-    V3 colour = mk(0, 0, 0);
-    int depth = 0;
-    int subPath = 0;
-    Surface primary{};
-    bool primarySpecular = false;
-    V3 acc = mk(0, 0, 0);
-    bool sampleDone = args.maxDepth <= 0; // radiance() returns Vec3() at once (Scene.cpp:128-129)
-
-    while (!sampleDone) { // the keyed megakernel's state machine, one path at a time
-      ++casts;
-      const Nearest best = warpIntersect<kOo>(scene, origin, direction, lane, true, true, inf);
-      bool ended = false, bounce = false, terminalPrimary = false;
-      V3 incoming = mk(0, 0, 0);
-      Surface surface{};
-      if (best.prim == kNoPrim) {
-        incoming = environment;
+    ++casts;
+    const Nearest best = groupIntersect<kGroup, kOo>(scene, origin, direction, glane, mask, true, true, inf);
+    bool ended = false, bounce = false, terminalPrimary = false;
+    V3 incoming = mk(0, 0, 0);
+    Surface surface{};
+    if (best.prim == kNoPrim) {
+      incoming = environment;
+      ended = true;
+    } else {
+      const HitInfo hit = finishHit(scene, scene.spheres, origin, direction, best);
+      const MaterialView mat = materialOf(scene, hit.material);
+      if (depth == 0 && args.preview) {
+        incoming = mat.diffuse();
         ended = true;
+      } else if (depth + 1 >= args.maxDepth) {
+        // The deepest level draws its (u, v, p) triples and builds rays whose radiance is
+        // Vec3() (Scene.cpp:128-129,157-175): consume the stream, contribute the emission.
+        rng.skip(6u * static_cast<uint32_t>(depth == 0 ? numSub : 1));
+        incoming = shadeTerm(mat, true, mk(0, 0, 0)); // oo: emission + (0 + .. + 0) * (1/n), the same value
+        ended = true;
+        terminalPrimary = depth == 0;
       } else {
-        const HitInfo hit = finishHit(scene, scene.spheres, origin, direction, best);
-        const MaterialView mat = materialOf(scene, hit.material);
-        if (depth == 0 && args.preview) {
-          incoming = mat.diffuse();
-          ended = true;
-        } else if (depth + 1 >= args.maxDepth) {
-          // The deepest level draws its (u, v, p) triples and builds rays whose radiance is
-          // Vec3() (Scene.cpp:128-129,157-175): consume the stream, contribute the emission.
-          rng.skip(6u * static_cast<uint32_t>(depth == 0 ? numSub : 1), lane);
-          incoming = shadeTerm(mat, true, mk(0, 0, 0)); // oo: emission + (0 + .. + 0) * (1/n), the same value
-          ended = true;
-          terminalPrimary = depth == 0;
+        surface.position = hit.position;
+        surface.normal = hit.normal;
+        surface.incoming = direction;
+        surface.material = hit.material;
+        surface.reflectivity = hitReflectivity(mat, hit, direction);
+        hitBasis(scene, hit, surface.basisX, surface.basisY);
+        if (depth == 0) {
+          primary = surface;
+          acc = mk(0, 0, 0);
+          subPath = 0;
+        }
+        bounce = true;
+      }
+    }
+    if (ended) {
+      colour = incoming;
+      if (depth == 0) {
+        if (terminalPrimary && !kOo) {
+          acc = mk(0, 0, 0);
+          for (int k = 0; k < numSub; ++k)
+            acc = add(acc, incoming);
+          colour = scale(acc, invNumSub);
+        }
+        sampleDone = true;
+      } else {
+        for (int level = depth - 1; level >= 1; --level) {
+          const MaterialView mat = materialOf(scene, stackMaterial[level]);
+          incoming = kOo ? ooLevelRadiance(mat, fpSubSampleTerm(mat, stackSpecular[level], incoming), 1.0)
+                         : shadeTerm(mat, stackSpecular[level], incoming);
+        }
+        const MaterialView primaryMat = materialOf(scene, primary.material);
+        acc = add(acc, kOo ? fpSubSampleTerm(primaryMat, primarySpecular, incoming)
+                           : shadeTerm(primaryMat, primarySpecular, incoming));
+        ++subPath;
+        if (subPath >= numSub) {
+          colour = kOo ? ooLevelRadiance(primaryMat, acc, invNumSub) // src/oo/Renderer.cpp:90
+                       : scale(acc, invNumSub);                      // Scene.cpp:178
+          sampleDone = true;
         } else {
-          surface.position = hit.position;
-          surface.normal = hit.normal;
-          surface.incoming = direction;
-          surface.material = hit.material;
-          surface.reflectivity = hitReflectivity(mat, hit, direction);
-          hitBasis(scene, hit, surface.basisX, surface.basisY);
-          if (depth == 0) {
-            primary = surface;
-            acc = mk(0, 0, 0);
-            subPath = 0;
-          }
+          depth = 0;
           bounce = true;
         }
       }
-      if (ended) {
-        colour = incoming;
-        if (depth == 0) {
-          if (terminalPrimary && !kOo) {
-            acc = mk(0, 0, 0);
-            for (int k = 0; k < numSub; ++k)
-              acc = add(acc, incoming);
-            colour = scale(acc, invNumSub);
-          }
-          sampleDone = true;
-        } else {
-          for (int level = depth - 1; level >= 1; --level) {
-            const MaterialView mat = materialOf(scene, stackMaterial[level]);
-            incoming = kOo ? ooLevelRadiance(mat, fpSubSampleTerm(mat, stackSpecular[level], incoming), 1.0)
-                           : shadeTerm(mat, stackSpecular[level], incoming);
-          }
-          const MaterialView primaryMat = materialOf(scene, primary.material);
-          acc = add(acc, kOo ? fpSubSampleTerm(primaryMat, primarySpecular, incoming)
-                             : shadeTerm(primaryMat, primarySpecular, incoming));
-          ++subPath;
-          if (subPath >= numSub) {
-            colour = kOo ? ooLevelRadiance(primaryMat, acc, invNumSub) // src/oo/Renderer.cpp:90
-                         : scale(acc, invNumSub);                      // Scene.cpp:178
-            sampleDone = true;
-          } else {
-            depth = 0;
-            bounce = true;
-          }
-        }
-      }
-      if (bounce) {
-        const bool fromPrimary = depth == 0;
-        if (fromPrimary)
-          surface = primary;
-        double ru, rv, rp; // u, v, p in this order (Scene.cpp:157-161)
-        rng.canonical3(lane, ru, rv, rp);
-        double u = ru, v = rv;
-        if (fromPrimary) {
-          u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
-          v = ieeeDiv(static_cast<double>(subPath % args.firstBounceV) + rv, static_cast<double>(args.firstBounceV));
-        }
-        const MaterialView mat = materialOf(scene, surface.material);
-        bool specular;
-        V3 newDirection;
-        if (rp < surface.reflectivity) {
-          newDirection = coneSample(reflect(surface.normal, surface.incoming), mat.coneAngle(), u, v);
-          specular = true;
-        } else {
-          newDirection = hemisphereSample(Basis{surface.basisX, surface.basisY, surface.normal}, u, v);
-          specular = false;
-        }
-        if (fromPrimary) {
-          primarySpecular = specular;
-        } else {
-          stackMaterial[depth] = static_cast<uint16_t>(surface.material);
-          stackSpecular[depth] = specular;
-        }
-        origin = surface.position;
-        direction = newDirection;
-        ++depth;
-      }
     }
-    if (lane == 0) {
-      double *dst = passSamples + 3 * static_cast<size_t>(pixelIndex);
-      dst[0] = colour.x;
-      dst[1] = colour.y;
-      dst[2] = colour.z;
+    if (bounce) {
+      const bool fromPrimary = depth == 0;
+      if (fromPrimary)
+        surface = primary;
+      double ru, rv, rp; // u, v, p in this order (Scene.cpp:157-161)
+      rng.canonical3(ru, rv, rp);
+      double u = ru, v = rv;
+      if (fromPrimary) {
+        u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
+        v = ieeeDiv(static_cast<double>(subPath % args.firstBounceV) + rv, static_cast<double>(args.firstBounceV));
+      }
+      const MaterialView mat = materialOf(scene, surface.material);
+      bool specular;
+      V3 newDirection;
+      if (rp < surface.reflectivity) {
+        newDirection = coneSample(reflect(surface.normal, surface.incoming), mat.coneAngle(), u, v);
+        specular = true;
+      } else {
+        newDirection = hemisphereSample(Basis{surface.basisX, surface.basisY, surface.normal}, u, v);
+        specular = false;
+      }
+      if (fromPrimary) {
+        primarySpecular = specular;
+      } else {
+        stackMaterial[depth] = static_cast<uint16_t>(surface.material);
+        stackSpecular[depth] = specular;
+      }
+      origin = surface.position;
+      direction = newDirection;
+      ++depth;
     }
   }
-  if (lane == 0)
+  if (glane == 0)
     atomicAdd(args.castCounter, static_cast<unsigned long long>(casts));
 }
 
@@ -1063,15 +1108,47 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
   }
 }
 
-cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream) {
-  const int blocks = (args.numPasses + kSequentialWarps - 1) / kSequentialWarps;
+// Lanes per pass of the sequential kernel.  A pass is one dependent chain, so the machine is filled by
+// passes alone: with few passes every pass gets a whole warp (the sweep is split 32 ways and the
+// chain is as short as it gets); once halving the group still leaves `kWarpsPerSmWanted` warps per
+// SM, the smaller group wins — the shading that a group computes redundantly is issued once per 16 /
+// 8 / 4 lanes instead of once per 32.  `requested` (PtRenderOptions.lanesPerPass or the environment
+// variable PTB200_SEQUENTIAL_LANES) overrides the choice.
+int sequentialLanesPerPass(int numPasses, int numSms, int requested) {
+  if (requested <= 0) {
+    const char *env = getenv("PTB200_SEQUENTIAL_LANES");
+    requested = env ? atoi(env) : 0;
+  }
+  if (requested == 4 || requested == 8 || requested == 16 || requested == 32)
+    return requested;
+  constexpr int kWarpsPerSmWanted = 8;
+  int group = 32;
+  while (group > 4 && static_cast<long long>(numPasses) * (group / 2) / 32 >= static_cast<long long>(numSms) * kWarpsPerSmWanted)
+    group /= 2;
+  return group;
+}
+
+template <int kGroup>
+static cudaError_t launchSequentialGroup(const SequentialArgs &args, cudaStream_t stream) {
+  constexpr int kPassesPerCta = kSequentialWarps * (32 / kGroup);
+  const int blocks = (args.numPasses + kPassesPerCta - 1) / kPassesPerCta;
   if (args.way == 2)
-    renderSequentialKernel<kSequentialWarps, true><<<blocks, kSequentialWarps * 32, 0, stream>>>(args);
+    renderSequentialKernel<kSequentialWarps, kGroup, true><<<blocks, kSequentialWarps * 32, 0, stream>>>(args);
   else if (args.way == 0)
-    renderSequentialKernel<kSequentialWarps, false><<<blocks, kSequentialWarps * 32, 0, stream>>>(args);
+    renderSequentialKernel<kSequentialWarps, kGroup, false><<<blocks, kSequentialWarps * 32, 0, stream>>>(args);
   else
     return cudaErrorInvalidValue;
   return cudaGetLastError();
+}
+
+cudaError_t launchRenderSequential(const SequentialArgs &args, int lanesPerPass, cudaStream_t stream) {
+  switch (lanesPerPass) {
+  case 32: return launchSequentialGroup<32>(args, stream);
+  case 16: return launchSequentialGroup<16>(args, stream);
+  case 8: return launchSequentialGroup<8>(args, stream);
+  case 4: return launchSequentialGroup<4>(args, stream);
+  default: return cudaErrorInvalidValue;
+  }
 }
 
 cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream) {

@@ -129,7 +129,8 @@ size_t splitBytesPerSample(uint32_t numSub);
 bool constTableFits(uint32_t numTriangles, uint32_t numTiles); // sweep variant 9 applies
 cudaError_t launchSplitTrace(const SplitArgs &args, int numSms, int config, cudaStream_t stream);   // 2 launches
 cudaError_t launchSplitResolve(const SplitArgs &args, cudaStream_t stream);                         // 1 launch
-cudaError_t launchRenderSequential(const SequentialArgs &args, cudaStream_t stream);
+int sequentialLanesPerPass(int numPasses, int numSms, int requested);
+cudaError_t launchRenderSequential(const SequentialArgs &args, int lanesPerPass, cudaStream_t stream);
 cudaError_t launchReducePasses(const ReduceArgs &args, cudaStream_t stream);
 cudaError_t launchIntersect(const IntersectArgs &args, cudaStream_t stream);
 cudaError_t launchFp64Peak(double *sink, int iterations, int blocks, int threads,

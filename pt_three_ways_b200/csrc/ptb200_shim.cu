@@ -220,6 +220,9 @@ int validateParams(const PtRenderParams *p, const PtRenderOptions *o) {
         (o->rowBegin != 0 || o->rowStep > 1))
       return fail(PTB200_EINVAL,
                   "the sequential mt19937 stream cannot be partitioned by rows; partition passes");
+    if (o->lanesPerPass != 0 && o->lanesPerPass != 4 && o->lanesPerPass != 8 && o->lanesPerPass != 16 &&
+        o->lanesPerPass != 32)
+      return fail(PTB200_EINVAL, "lanesPerPass must be 0 (automatic), 4, 8, 16 or 32, not %d", o->lanesPerPass);
   }
   return PTB200_OK;
 }
@@ -593,7 +596,7 @@ static int enqueueRender(PtContext *ctx, const PtCamera *camera, const PtRenderP
       a.way = ooWay ? 2 : 0;
       a.samples = ctx->samples.ptr;
       a.castCounter = ctx->counters.ptr + 1;
-      PT_CUDA(launchRenderSequential(a, ctx->stream));
+      PT_CUDA(launchRenderSequential(a, sequentialLanesPerPass(batch, ctx->numSms, opt.lanesPerPass), ctx->stream));
     } else if (split) {
       // Batch b traces on the stream of buffer set b % 2 — after the resolve that last read the set
       // — and resolves on ctx->stream, in batch order: passes are added in pass order.

@@ -136,6 +136,53 @@ def test_render_matches_oracle(case, mode_name, scenes, oracle, capi):
     assert np.array_equal(pixels["sum"], want["sums"])
 
 
+# The exact-stream policies with a pass shared by 4 / 8 / 16 / 32 lanes (PtRenderOptions.lanesPerPass):
+# pass counts that leave the last warp and the last CTA partly filled, every estimator branch.
+LANE_GROUP_CASES = [
+    ("cornell", 24, 18, 9, 1, {}),
+    ("cornell", 20, 15, 17, 5, dict(first_u=2, first_v=3, max_depth=3)),
+    ("cornell", 16, 12, 5, 9, dict(max_depth=1)),
+    ("cornell", 16, 12, 3, 9, dict(preview=1)),
+    ("cornell", 12, 9, 6, 4, dict(max_depth=7)),
+    ("multi-sphere", 24, 18, 7, 4, {}),
+    ("suzanne", 16, 12, 3, 2, {}),
+    ("ce", 8, 6, 2, 7, {}),
+]
+
+
+@pytest.mark.parametrize("lanes", [4, 8, 16, 32])
+@pytest.mark.parametrize("mode_name", ["sequential", "oo"])
+@pytest.mark.parametrize("case", LANE_GROUP_CASES, ids=lambda c: f"{c[0]}-{c[3]}passes-{len(c[5])}{c[5].get('max_depth', '')}")
+def test_sequential_lane_groups_match_oracle(case, mode_name, lanes, scenes, oracle, capi):
+    name, w, h, spp, seed, kw = case
+    mode, oracle_mode = ((capi.RNG_MT19937_SEQUENTIAL, oracle.RNG_MT19937_SEQUENTIAL) if mode_name == "sequential"
+                         else (capi.RNG_MT19937_SEQUENTIAL_OO, oracle.RNG_OO_SEQUENTIAL))
+    scene = scenes[name]
+    camera = scene.camera(w, h)
+    pixels, stats = capi.render(scene, camera, capi.make_params(w, h, spp=spp, seed=seed, **kw),
+                                capi.make_options(rng_mode=mode, lanes_per_pass=lanes))
+    want = oracle.OracleScene(scene).render(camera, oracle.params_array(w, h, spp=spp, seed=seed, **kw),
+                                            oracle_mode, threads=4)
+    assert np.array_equal(pixels["n"], want["counts"])
+    assert stats["casts"] == want["casts"]
+    assert np.array_equal(pixels["sum"], want["sums"])  # bit-exact
+
+
+def test_sequential_lane_group_is_chosen_from_the_pass_count(scenes, capi):
+    """Many passes on a small frame: the library picks a sub-warp group by itself, and the image is
+    the one a warp per pass renders."""
+    scene = scenes["cornell"]
+    w, h, spp = 6, 4, 2500
+    cam = scene.camera(w, h)
+    params = capi.make_params(w, h, spp=spp, seed=11)
+    auto, sa = capi.render(scene, cam, params, capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL))
+    full, sf = capi.render(scene, cam, params, capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL, lanes_per_pass=32))
+    assert sa["casts"] == sf["casts"]
+    assert np.array_equal(auto["sum"], full["sum"]) and (auto["n"] == spp).all()
+    with pytest.raises(capi.Ptb200Error):
+        capi.render(scene, cam, params, capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL, lanes_per_pass=5))
+
+
 # ---- size-independent properties at BASELINE.json's full sizes ---------------------------------
 def test_full_size_config1_properties(scenes, capi):
     """CornellBox 640x480 @ 256 spp (BASELINE configs[1]) is too big for the CPU oracle, so it is

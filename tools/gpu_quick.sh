@@ -1,11 +1,6 @@
 #!/bin/bash
-# Scratch A/B session.
+# Scratch session: lane groups of the exact-stream policies.
 OUT=gpurun_out
 mkdir -p $OUT
-true
-for scene in "suzanne 640 480 32" "ce 1280 720 4" "cornell 640 480 64"; do
-  set -- $scene
-  cfgs="217,127"; [ "$1" = cornell ] && cfgs="128,127"
-  echo "== $scene (fan groups)"; SWEEP_CONFIGS="$cfgs" SWEEP_SEQUENTIAL=0 timeout 600 python tools/sweep_configs.py $scene 2>&1 | cut -c1-170
-  echo "== $scene (PTB200_NO_FAN_GROUPS=1)"; PTB200_NO_FAN_GROUPS=1 SWEEP_CONFIGS="$cfgs" SWEEP_SEQUENTIAL=0 timeout 600 python tools/sweep_configs.py $scene 2>&1 | cut -c1-170
-done
+echo "== parity"; timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_oo_way.py -m gpu -x -q -k "lane_group or sequential or oo_way" 2>&1 | tail -4 | tee $OUT/r2p_seq_tests.log
+echo "== rates"; timeout 900 python tools/sequential_rates.py cornell 160 120 256,4096 0,32,16,8,4 2>&1 | tee $OUT/r2p_sequential_rates.jsonl
