@@ -418,108 +418,51 @@ __device__ __forceinline__ unsigned groupMaskOf(unsigned lane) {
   return kGroup == 32 ? kFullMask : ((1u << (kGroup & 31)) - 1u) << (lane & ~static_cast<unsigned>(kGroup - 1));
 }
 
-// std::mt19937 with its state in shared memory, one instance per pass; `index` is uniform over
-// the group's lanes.
+// uniform_real_distribution<double> draws from a pass's engine (pt_mt19937.cuh: GroupMt19937).  Two /
+// three canonical doubles at once: when they do not straddle the end of a generation the state words
+// are read independently instead of through dependent next() calls.
 template <int kGroup>
-struct GroupMt19937 {
-  uint32_t *state; // 624 words
-  int index;
-  unsigned mask;   // the lanes of this group
-  unsigned glane;  // lane within the group
+__device__ __forceinline__ double mtCanonical(GroupMt19937<kGroup> &rng) {
+  const uint32_t lo = rng.next();
+  const uint32_t hi = rng.next();
+  return canonicalFromWords(lo, hi);
+}
+template <int kGroup>
+__device__ __forceinline__ void mtCanonical2(GroupMt19937<kGroup> &rng, double &a, double &b) {
+  if (rng.index + 4 <= 624) {
+    const uint32_t *w = rng.state + rng.index;
+    const uint32_t w0 = rng.temper(w[0]), w1 = rng.temper(w[1]), w2 = rng.temper(w[2]), w3 = rng.temper(w[3]);
+    rng.index += 4;
+    a = canonicalFromWords(w0, w1);
+    b = canonicalFromWords(w2, w3);
+  } else {
+    a = mtCanonical(rng);
+    b = mtCanonical(rng);
+  }
+}
+template <int kGroup>
+__device__ __forceinline__ void mtCanonical3(GroupMt19937<kGroup> &rng, double &a, double &b, double &c) {
+  if (rng.index + 6 <= 624) {
+    const uint32_t *w = rng.state + rng.index;
+    const uint32_t w0 = rng.temper(w[0]), w1 = rng.temper(w[1]), w2 = rng.temper(w[2]), w3 = rng.temper(w[3]),
+                   w4 = rng.temper(w[4]), w5 = rng.temper(w[5]);
+    rng.index += 6;
+    a = canonicalFromWords(w0, w1);
+    b = canonicalFromWords(w2, w3);
+    c = canonicalFromWords(w4, w5);
+  } else {
+    a = mtCanonical(rng);
+    b = mtCanonical(rng);
+    c = mtCanonical(rng);
+  }
+}
 
-  __device__ __forceinline__ void seed(uint32_t value) {
-    if (glane == 0) {
-      uint32_t x = value;
-      state[0] = x;
-      for (int i = 1; i < 624; ++i) {
-        x = 1812433253u * (x ^ (x >> 30)) + static_cast<uint32_t>(i);
-        state[i] = x;
-      }
-    }
-    index = 624;
-    __syncwarp(mask);
-  }
-  // The twist, kGroup words at a time in index order; loads precede stores within a batch, so
-  // word i sees old[i], old[i+1] and (i < 227 ? old : new)[i+397 mod 624] as the serial
-  // algorithm does (a batch is at most 32 < 227 words).
-  __device__ __noinline__ void refill() {
-    for (int batch = 0; batch < 624; batch += kGroup) {
-      const int i = batch + static_cast<int>(glane);
-      uint32_t value = 0;
-      if (i < 624) {
-        const uint32_t y = (state[i] & 0x80000000u) | (state[(i + 1) % 624] & 0x7fffffffu);
-        value = state[(i + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-      }
-      __syncwarp(mask);
-      if (i < 624)
-        state[i] = value;
-      __syncwarp(mask);
-    }
-    index = 0;
-  }
-  __device__ __forceinline__ static uint32_t temper(uint32_t y) {
-    y ^= y >> 11;
-    y ^= (y << 7) & 0x9d2c5680u;
-    y ^= (y << 15) & 0xefc60000u;
-    y ^= y >> 18;
-    return y;
-  }
-  __device__ __forceinline__ uint32_t next() {
-    if (index >= 624)
-      refill();
-    return temper(state[index++]);
-  }
-  __device__ __forceinline__ double canonical() {
-    const uint32_t lo = next();
-    const uint32_t hi = next();
-    return canonicalFromWords(lo, hi);
-  }
-  // Two / three canonical doubles at once: when they do not straddle a refill the state words are
-  // read independently instead of through dependent next() calls.
-  __device__ __forceinline__ void canonical2(double &a, double &b) {
-    if (index + 4 <= 624) {
-      const uint32_t w0 = temper(state[index]), w1 = temper(state[index + 1]), w2 = temper(state[index + 2]),
-                     w3 = temper(state[index + 3]);
-      index += 4;
-      a = canonicalFromWords(w0, w1);
-      b = canonicalFromWords(w2, w3);
-    } else {
-      a = canonical();
-      b = canonical();
-    }
-  }
-  __device__ __forceinline__ void canonical3(double &a, double &b, double &c) {
-    if (index + 6 <= 624) {
-      const uint32_t w0 = temper(state[index]), w1 = temper(state[index + 1]), w2 = temper(state[index + 2]),
-                     w3 = temper(state[index + 3]), w4 = temper(state[index + 4]), w5 = temper(state[index + 5]);
-      index += 6;
-      a = canonicalFromWords(w0, w1);
-      b = canonicalFromWords(w2, w3);
-      c = canonicalFromWords(w4, w5);
-    } else {
-      a = canonical();
-      b = canonical();
-      c = canonical();
-    }
-  }
-  // Discards `count` outputs.
-  __device__ __forceinline__ void skip(uint32_t count) {
-    while (count) {
-      if (index >= 624)
-        refill();
-      const uint32_t step = min(count, static_cast<uint32_t>(624 - index));
-      index += static_cast<int>(step);
-      count -= step;
-    }
-  }
-};
-
-// Scene::intersect by a group of kGroup lanes: the lanes stride the primitive lists, then an argmin
-// over the group.  kAcceptEpsilon: oo::Triangle::intersect (src/oo/Triangle.cpp:31) rejects
+// Scene::intersect by a group of kGroup lanes: the lanes stride the primitive lists (groupSweep), then
+// an argmin over the group (groupArgmin).  kAcceptEpsilon: oo::Triangle::intersect (src/oo/Triangle.cpp:31) rejects
 // `t < Epsilon` where Scene.cpp:94 accepts `t > Epsilon`.
 template <int kGroup, bool kAcceptEpsilon = false>
-__device__ __forceinline__ Nearest groupIntersect(const DeviceScene &scene, V3 o, V3 d, unsigned glane, unsigned mask,
-                                                  bool useSpheres, bool useTriangles, double nearerThanLimit) {
+__device__ __forceinline__ Nearest groupSweep(const DeviceScene &scene, V3 o, V3 d, unsigned glane, bool useSpheres,
+                                              bool useTriangles, double nearerThanLimit) {
   Nearest best{nearerThanLimit, 0.0, kNoPrim};
   if (useSpheres) {
     for (uint32_t i = glane; i < scene.numSpheres; i += kGroup) {
@@ -544,11 +487,13 @@ __device__ __forceinline__ Nearest groupIntersect(const DeviceScene &scene, V3 o
   if (useTriangles) {
     // A triangle only replaces a sphere hit when strictly nearer, which the argmin's ordering
     // below encodes; per lane the strict `<` keeps the lowest index among equals.
-    // One 80-byte AoS record per triangle (triExact); padding records are all-zero (det == 0)
-    // and reject themselves.  (Unrolling this loop by two was measured: 10 % slower.)
-    const uint32_t slots = scene.numTiles * scene.tileTris;
+    // One 80-byte AoS record per triangle (triExact), tiles back to back: only the last one is padded,
+    // so the real triangles are the first numTriangles slots (a padding record would reject itself,
+    // det == 0, after a trip through the division's slow path).
+    // (Testing two or four records per lane and trip side by side was measured: no gain, r2q — the
+    // kernel waits on the shading chain, not on the trips.)
 #pragma unroll 1
-    for (uint32_t index = glane; index < slots; index += kGroup) {
+    for (uint32_t index = glane; index < scene.numTriangles; index += kGroup) {
       const double2 *record = reinterpret_cast<const double2 *>(scene.triExact + 10 * static_cast<size_t>(index));
       const double2 a0 = __ldg(record), a1 = __ldg(record + 1), a2 = __ldg(record + 2), a3 = __ldg(record + 3),
                     a4 = __ldg(record + 4);
@@ -556,23 +501,50 @@ __device__ __forceinline__ Nearest groupIntersect(const DeviceScene &scene, V3 o
                                    static_cast<int>(index), best);
     }
   }
-  // Group argmin in the serial scans' order (t, sphere-before-triangle, index) with three
-  // integer min-reductions: hit distances are positive, so their bit patterns order like
-  // unsigned integers.
+  return best;
+}
+
+// The group's nearest hit in the serial scans' order (t, sphere-before-triangle, index); hit distances
+// are positive, so their bit patterns order like unsigned integers.  Every lane of the WARP must call
+// it (a lane without a ray passes Nearest{inf, 0, kNoPrim}).
+template <int kGroup>
+__device__ __forceinline__ Nearest groupArgmin(Nearest best, unsigned mask) {
   const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(best.t));
-  const uint32_t hi = static_cast<uint32_t>(bits >> 32), lo = static_cast<uint32_t>(bits);
-  const uint32_t minHi = __reduce_min_sync(mask, hi);
-  const uint32_t minLo = __reduce_min_sync(mask, hi == minHi ? lo : 0xffffffffu);
-  const bool nearest = hi == minHi && lo == minLo;
   const uint32_t order = best.prim == kNoPrim ? 0xffffffffu
                          : best.prim < 0      ? static_cast<uint32_t>(-best.prim - 1)
                                               : 0x40000000u + static_cast<uint32_t>(best.prim);
-  const uint32_t minOrder = __reduce_min_sync(mask, nearest ? order : 0xffffffffu);
-  const int winner = __ffs(__ballot_sync(mask, nearest && order == minOrder)) - 1; // a lane of the warp
-  best.t = __shfl_sync(mask, best.t, winner);
-  best.det = __shfl_sync(mask, best.det, winner);
-  best.prim = __shfl_sync(mask, best.prim, winner);
+  int winner;
+  if (kGroup == 32) { // three integer min-reductions (REDUX)
+    const uint32_t hi = static_cast<uint32_t>(bits >> 32), lo = static_cast<uint32_t>(bits);
+    const uint32_t minHi = __reduce_min_sync(kFullMask, hi);
+    const uint32_t minLo = __reduce_min_sync(kFullMask, hi == minHi ? lo : 0xffffffffu);
+    const bool nearest = hi == minHi && lo == minLo;
+    const uint32_t minOrder = __reduce_min_sync(kFullMask, nearest ? order : 0xffffffffu);
+    winner = __ffs(__ballot_sync(kFullMask, nearest && order == minOrder)) - 1;
+  } else { // a butterfly inside each group: REDUX on a partial mask is emulated, shuffles are not
+    unsigned long long minBits = bits;
+    uint32_t minOrder = order;
+#pragma unroll
+    for (int offset = 1; offset < kGroup; offset <<= 1) {
+      const unsigned long long otherBits = __shfl_xor_sync(kFullMask, minBits, offset);
+      const uint32_t otherOrder = __shfl_xor_sync(kFullMask, minOrder, offset);
+      const bool less = otherBits < minBits || (otherBits == minBits && otherOrder < minOrder);
+      minBits = less ? otherBits : minBits;
+      minOrder = less ? otherOrder : minOrder;
+    }
+    winner = __ffs(__ballot_sync(kFullMask, bits == minBits && order == minOrder) & mask) - 1; // a lane of the warp
+  }
+  best.t = __shfl_sync(kFullMask, best.t, winner);
+  best.det = __shfl_sync(kFullMask, best.det, winner);
+  best.prim = __shfl_sync(kFullMask, best.prim, winner);
   return best;
+}
+
+template <int kGroup, bool kAcceptEpsilon = false>
+__device__ __forceinline__ Nearest groupIntersect(const DeviceScene &scene, V3 o, V3 d, unsigned glane, unsigned mask,
+                                                  bool useSpheres, bool useTriangles, double nearerThanLimit) {
+  return groupArgmin<kGroup>(groupSweep<kGroup, kAcceptEpsilon>(scene, o, d, glane, useSpheres, useTriangles, nearerThanLimit),
+                             mask);
 }
 
 template <bool kAcceptEpsilon = false>
@@ -598,6 +570,7 @@ __global__ void __launch_bounds__(kWarps * 32)
     renderSequentialKernel(const __grid_constant__ SequentialArgs args) {
   constexpr int kPassesPerWarp = 32 / kGroup;
   __shared__ uint32_t mtState[kWarps * kPassesPerWarp][624];
+  __shared__ Surface primarySlots[kWarps * kPassesPerWarp];
   const DeviceScene &scene = args.scene;
   const unsigned lane = threadIdx.x & 31u;
   const unsigned warp = threadIdx.x >> 5;
@@ -606,13 +579,19 @@ __global__ void __launch_bounds__(kWarps * 32)
   const unsigned mask = groupMaskOf<kGroup>(lane);
   const int passInBatch = (static_cast<int>(blockIdx.x) * kWarps + static_cast<int>(warp)) * kPassesPerWarp +
                           static_cast<int>(groupInWarp);
-  if (passInBatch >= args.numPasses)
-    return;
-  GroupMt19937<kGroup> rng{mtState[warp * kPassesPerWarp + groupInWarp], 624, mask, glane};
-  rng.seed(static_cast<uint32_t>(args.seed + args.passBegin + passInBatch));
+  // A group without a pass (the tail of the last CTA) stays with its warp: the loop below is uniform
+  // over the WARP, so that its groups meet again every iteration and sweep together.
+  const bool hasPass = passInBatch < args.numPasses;
+  GroupMt19937<kGroup> rng{mtState[warp * kPassesPerWarp + groupInWarp], 0, 0, mask, glane};
+  if (hasPass)
+    rng.seed(static_cast<uint32_t>(args.seed + args.passBegin + passInBatch));
 
   const int numSub = args.firstBounceU * args.firstBounceV;
   const double invNumSub = 1.0 / static_cast<double>(numSub);
+  const bool uPow2 = (args.firstBounceU & (args.firstBounceU - 1)) == 0;
+  const bool vPow2 = (args.firstBounceV & (args.firstBounceV - 1)) == 0;
+  const double invFirstBounceU = 1.0 / static_cast<double>(args.firstBounceU);
+  const double invFirstBounceV = 1.0 / static_cast<double>(args.firstBounceV);
   const V3 environment = mk(scene.environment[0], scene.environment[1], scene.environment[2]);
   const double inf = __longlong_as_double(0x7ff0000000000000ll);
   double *passSamples = args.samples + static_cast<size_t>(passInBatch) * args.width * args.height * 3;
@@ -628,40 +607,54 @@ __global__ void __launch_bounds__(kWarps * 32)
   V3 colour = mk(0, 0, 0);
   int depth = 0;
   int subPath = 0;
-  Surface primary{};
+  // The camera ray's surface waits in shared memory while the sample's sub-paths are traced: every lane
+  // of the group stores the same bytes and reads back what it stored itself, so no barrier is needed.
+  Surface &primary = primarySlots[warp * kPassesPerWarp + groupInWarp];
   bool primarySpecular = false;
   V3 acc = mk(0, 0, 0);
   bool sampleDone = true;
+  bool finished = !hasPass;
 
   for (;;) { // the keyed megakernel's state machine, one path at a time per group
-    if (sampleDone) { // store the finished pixel, start the next one: row-major (Scene.cpp:212-213)
+    if (sampleDone && !finished) { // store the finished pixel, start the next one: row-major (Scene.cpp:212-213)
       if (pixelIndex >= 0 && glane == 0) {
         double *dst = passSamples + 3 * static_cast<size_t>(pixelIndex);
         dst[0] = colour.x;
         dst[1] = colour.y;
         dst[2] = colour.z;
       }
-      if (++pixelIndex >= numPixels)
-        break;
-      if (++px == args.width) {
-        px = 0;
-        ++py;
+      if (++pixelIndex >= numPixels) {
+        finished = true;
+      } else {
+        if (++px == args.width) {
+          px = 0;
+          ++py;
+        }
+        // Camera::randomRay draws before radiance() looks at the depth (Scene.cpp:214-215).
+        double ux, uy, ua = 0, ur = 0;
+        mtCanonical2(rng, ux, uy);
+        if (args.camera.apertureRadius != 0)
+          mtCanonical2(rng, ua, ur);
+        cameraRay(args.camera, px, py, ux, uy, ua, ur, origin, direction);
+        colour = mk(0, 0, 0);
+        depth = 0;
+        subPath = 0;
+        sampleDone = args.maxDepth <= 0; // radiance() returns Vec3() at once (Scene.cpp:128-129)
       }
-      // Camera::randomRay draws before radiance() looks at the depth (Scene.cpp:214-215).
-      double ux, uy, ua = 0, ur = 0;
-      rng.canonical2(ux, uy);
-      if (args.camera.apertureRadius != 0)
-        rng.canonical2(ua, ur);
-      cameraRay(args.camera, px, py, ux, uy, ua, ur, origin, direction);
-      colour = mk(0, 0, 0);
-      depth = 0;
-      subPath = 0;
-      sampleDone = args.maxDepth <= 0; // radiance() returns Vec3() at once (Scene.cpp:128-129)
-      if (sampleDone)
-        continue;
     }
+    if (__all_sync(kFullMask, finished))
+      break;
+    // The warp's groups are together here: they twist their consumed words, sweep and take the group
+    // minimum side by side; a group between two pixels (maxDepth <= 0) or past its last one idles.
+    const bool casting = !(finished || sampleDone);
+    rng.advance();
+    Nearest best{inf, 0.0, kNoPrim};
+    if (casting)
+      best = groupSweep<kGroup, kOo>(scene, origin, direction, glane, true, true, inf);
+    best = groupArgmin<kGroup>(best, mask);
+    if (!casting)
+      continue;
     ++casts;
-    const Nearest best = groupIntersect<kGroup, kOo>(scene, origin, direction, glane, mask, true, true, inf);
     bool ended = false, bounce = false, terminalPrimary = false;
     V3 incoming = mk(0, 0, 0);
     Surface surface{};
@@ -731,11 +724,14 @@ __global__ void __launch_bounds__(kWarps * 32)
       if (fromPrimary)
         surface = primary;
       double ru, rv, rp; // u, v, p in this order (Scene.cpp:157-161)
-      rng.canonical3(ru, rv, rp);
+      mtCanonical3(rng, ru, rv, rp);
       double u = ru, v = rv;
       if (fromPrimary) {
-        u = ieeeDiv(static_cast<double>(subPath / args.firstBounceV) + ru, static_cast<double>(args.firstBounceU));
-        v = ieeeDiv(static_cast<double>(subPath % args.firstBounceV) + rv, static_cast<double>(args.firstBounceV));
+        // a division by a power of two is the multiplication by its (exact) reciprocal, bit for bit
+        const double su = static_cast<double>(subPath / args.firstBounceV) + ru;
+        const double sv = static_cast<double>(subPath % args.firstBounceV) + rv;
+        u = uPow2 ? su * invFirstBounceU : ieeeDiv(su, static_cast<double>(args.firstBounceU));
+        v = vPow2 ? sv * invFirstBounceV : ieeeDiv(sv, static_cast<double>(args.firstBounceV));
       }
       const MaterialView mat = materialOf(scene, surface.material);
       bool specular;
@@ -1108,12 +1104,29 @@ cudaError_t launchRenderKeyed(const KeyedArgs &args, int numSms, int config, cud
   }
 }
 
+template <int kGroup>
+static int sequentialOccupancy() {
+  int ctas = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, renderSequentialKernel<kSequentialWarps, kGroup, false>,
+                                                    kSequentialWarps * 32, 0) != cudaSuccess || ctas < 1)
+    ctas = 5;
+  return ctas * kSequentialWarps;
+}
+static int sequentialWarpsPerSm(int group) {
+  static const int warps[4] = {sequentialOccupancy<4>(), sequentialOccupancy<8>(), sequentialOccupancy<16>(),
+                               sequentialOccupancy<32>()};
+  return warps[group == 4 ? 0 : group == 8 ? 1 : group == 16 ? 2 : 3];
+}
+
 // Lanes per pass of the sequential kernel.  A pass is one dependent chain, so the machine is filled by
-// passes alone: with few passes every pass gets a whole warp (the sweep is split 32 ways and the
-// chain is as short as it gets); once halving the group still leaves `kWarpsPerSmWanted` warps per
-// SM, the smaller group wins — the shading that a group computes redundantly is issued once per 16 /
-// 8 / 4 lanes instead of once per 32.  `requested` (PtRenderOptions.lanesPerPass or the environment
-// variable PTB200_SEQUENTIAL_LANES) overrides the choice.
+// passes alone and a launch is latency-bound until every SM holds its `residentWarps`.  With few passes
+// every pass gets a whole warp: the sweep is split 32 ways and the chain is as short as it gets (2.2 us
+// per cast on the Cornell box; 3.0 / 3.9 / 5.0 us with 16 / 8 / 4 lanes, whose 2 / 4 / 8 passes per warp
+// diverge in the shading).  More passes than resident warps would run in waves, so the group is the
+// largest one that keeps the launch in ONE wave: 4096 passes on 8 lanes are 1024 warps side by side
+// (21.5 Msamples/s) where a warp per pass takes 2.3 waves (12.3).  Measured: profiles/README.md r2r.
+// `requested` (PtRenderOptions.lanesPerPass or the environment variable PTB200_SEQUENTIAL_LANES)
+// overrides the choice.
 int sequentialLanesPerPass(int numPasses, int numSms, int requested) {
   if (requested <= 0) {
     const char *env = getenv("PTB200_SEQUENTIAL_LANES");
@@ -1121,9 +1134,10 @@ int sequentialLanesPerPass(int numPasses, int numSms, int requested) {
   }
   if (requested == 4 || requested == 8 || requested == 16 || requested == 32)
     return requested;
-  constexpr int kWarpsPerSmWanted = 8;
+  // the largest group whose launch fits the warps its own kernel keeps resident
   int group = 32;
-  while (group > 4 && static_cast<long long>(numPasses) * (group / 2) / 32 >= static_cast<long long>(numSms) * kWarpsPerSmWanted)
+  while (group > 4 && static_cast<long long>(numPasses) * group / 32 >
+                          static_cast<long long>(numSms) * sequentialWarpsPerSm(group))
     group /= 2;
   return group;
 }

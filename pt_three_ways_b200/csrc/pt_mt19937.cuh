@@ -144,4 +144,114 @@ struct LaneMt19937 {
   }
 };
 
+// std::mt19937 with its state in shared memory, one instance per pass; `index` and `regen` are uniform
+// over the group's lanes.
+//
+// Sub-warp groups twist LAZILY.  The textbook engine regenerates all 624 words when the last one has
+// been consumed — 78 batches on 8 lanes, while the other groups of the warp wait.  Word j of the next
+// generation only needs old[j], old[j+1] and (j < 227 ? old : new)[(j+397) mod 624], so a consumed word
+// can be regenerated at once, in index order: words [0, regen) already belong to the next generation,
+// [regen, index) are consumed, [index, 624) are still to be drawn.  advance() runs where the warp's
+// groups are together (the top of the state machine's loop) and regenerates the full batches of kGroup
+// words behind `index`: one 19-instruction batch per iteration serves every group of the warp at once.
+// wrap() completes the generation when `index` reaches 624.  A whole warp (kGroup == 32: 624 is not a
+// multiple of the batch) keeps the bulk twist.
+template <int kGroup>
+struct GroupMt19937 {
+  uint32_t *state; // 624 words
+  int index;       // next word to draw
+  int regen;       // next word to regenerate (kGroup < 32)
+  unsigned mask;   // the lanes of this group
+  unsigned glane;  // lane within the group
+
+  PT_HD void seed(uint32_t value) {
+    if (glane == 0) {
+      uint32_t x = value;
+      state[0] = x;
+      for (int i = 1; i < 624; ++i) {
+        x = 1812433253u * (x ^ (x >> 30)) + static_cast<uint32_t>(i);
+        state[i] = x;
+      }
+    }
+    index = 624; // every word "consumed": the first draw twists the seed words
+    regen = 0;
+    syncGroup();
+  }
+  // Twists words [first, first + kGroup) in place; loads precede stores within the batch, so word i
+  // sees old[i], old[i+1] and (i < 227 ? old : new)[i+397 mod 624] as the serial algorithm does (a
+  // batch is at most 32 < 227 words).  Only a whole warp's last batch runs past 624.
+  static PT_HD uint32_t twistedWord(const uint32_t *state, int i) {
+    const int next = i + 1 == 624 ? 0 : i + 1;
+    const int far = i < 227 ? i + 397 : i - 227;
+    const uint32_t y = (state[i] & 0x80000000u) | (state[next] & 0x7fffffffu);
+    return state[far] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+  }
+  PT_HD void syncGroup() {
+#ifdef __CUDA_ARCH__
+    __syncwarp(mask);
+#endif
+  }
+  PT_HD void twistBatch(int first) {
+#ifdef __CUDA_ARCH__
+    const int i = first + static_cast<int>(glane);
+    uint32_t value = 0;
+    if (kGroup < 32 || i < 624)
+      value = twistedWord(state, i);
+    __syncwarp(mask);
+    if (kGroup < 32 || i < 624)
+      state[i] = value;
+    __syncwarp(mask);
+#else // the host unit test plays every lane of the group: all loads, then all stores
+    uint32_t values[kGroup];
+    for (int lane = 0; lane < kGroup; ++lane)
+      values[lane] = first + lane < 624 ? twistedWord(state, first + lane) : 0u;
+    for (int lane = 0; lane < kGroup; ++lane)
+      if (first + lane < 624)
+        state[first + lane] = values[lane];
+#endif
+  }
+  // Regenerates the full batches among the consumed words; call it where the warp is converged.
+  PT_HD void advance() {
+    if (kGroup < 32) {
+      while (index - regen >= kGroup) {
+        twistBatch(regen);
+        regen += kGroup;
+      }
+    }
+  }
+  // index == 624: completes the generation and starts drawing from it.
+#ifdef __CUDACC__
+  __host__ __device__ __noinline__
+#endif
+  void wrap() {
+    for (int first = kGroup < 32 ? regen : 0; first < 624; first += kGroup)
+      twistBatch(first);
+    index = 0;
+    regen = 0;
+  }
+  static PT_HD uint32_t temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+  }
+  PT_HD uint32_t next() {
+    if (index >= 624)
+      wrap();
+    return temper(state[index++]);
+  }
+  // Discards `count` outputs.
+  PT_HD void skip(uint32_t count) {
+    while (count) {
+      if (index >= 624)
+        wrap();
+      const uint32_t room = static_cast<uint32_t>(624 - index);
+      const uint32_t step = count < room ? count : room;
+      index += static_cast<int>(step);
+      count -= step;
+    }
+  }
+};
+
 } // namespace ptb200

@@ -493,6 +493,40 @@ static void laneMt19937Tests() {
   CHECK(last == 4123659995u);
 }
 
+// The exact-stream policies' engine (csrc/pt_mt19937.cuh: GroupMt19937) against std::mt19937: the
+// lazy twist of sub-warp groups under every interleaving of advance(), draws and skips; the host build
+// plays all lanes of a group (loads of a batch before its stores).
+template <int kGroup>
+static void groupMt19937Case() {
+  std::mt19937 pattern(static_cast<uint32_t>(kGroup));
+  for (uint32_t seed : {0u, 1u, 5489u, 123456789u}) {
+    uint32_t state[624];
+    GroupMt19937<kGroup> rng{state, 0, 0, 0xffffffffu, 0u};
+    rng.seed(seed);
+    std::mt19937 reference(seed);
+    int bad = 0;
+    for (int iteration = 0; iteration < 60000; ++iteration) {
+      if (pattern() % 3)
+        rng.advance();
+      if (pattern() % 50 == 0) { // radiance() at the deepest level discards whole triples
+        const uint32_t count = pattern() % 2000;
+        rng.skip(count);
+        reference.discard(count);
+      }
+      for (uint32_t draws = pattern() % 14; draws; --draws)
+        bad += rng.next() != reference();
+      bad += rng.regen > rng.index || (kGroup < 32 && rng.regen % kGroup != 0);
+    }
+    CHECK(bad == 0);
+  }
+}
+static void groupMt19937Tests() {
+  groupMt19937Case<4>();
+  groupMt19937Case<8>();
+  groupMt19937Case<16>();
+  groupMt19937Case<32>();
+}
+
 int main(int argc, char **argv) {
   std::string scenesDir = "/root/reference/scenes", fixtureDir = "tests/golden/scenes";
   for (int i = 1; i + 1 < argc; i += 2) {
@@ -507,6 +541,7 @@ int main(int argc, char **argv) {
   sceneAdaptorTests();
   pngWriterTests();
   laneMt19937Tests();
+  groupMt19937Tests();
   int32_t deviceCount = 0;
   ptb200_device_count(&deviceCount);
   if (deviceCount > 0)
