@@ -469,6 +469,12 @@ def run_ours(args):
                 "parity": "bit-exact vs the oracle's sequential policy, which equals the reference's "
                           "per-pass images (tests/test_oracle_golden.py)",
                 "note": "parallel over passes only (SURVEY.md section 0 item 3); not the timed headline"}
+            many = 4096  # a launch that fills the machine: sub-warp pass groups (PtRenderOptions.lanesPerPass = 0)
+            est = ctx.render(scene.camera(ew, eh), capi.make_params(ew, eh, spp=many, seed=SEED),
+                             capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL, device=local_rank))
+            line["exact_stream_mode"]["at_4096_passes"] = {
+                "value": est["samples"] / est["kernel_ms"] / 1e3, "unit": UNIT,
+                "sample": f"cornell {ew}x{eh}, {many} passes, lanes per pass chosen by the library"}
             fst = ctx.render(camera, capi.make_params(width, height, spp=spp, seed=SEED),
                              capi.make_options(rng_mode=capi.RNG_MT19937_PER_PIXEL, device=local_rank))
             line["fp_way_mode"] = {

@@ -152,7 +152,7 @@ struct LaneMt19937 {
 // generation only needs old[j], old[j+1] and (j < 227 ? old : new)[(j+397) mod 624], so a consumed word
 // can be regenerated at once, in index order: words [0, regen) already belong to the next generation,
 // [regen, index) are consumed, [index, 624) are still to be drawn.  advance() runs where the warp's
-// groups are together (the top of the state machine's loop) and regenerates the full batches of kGroup
+// groups are together (the top of the state machine's loop) and regenerates a full batch of kGroup
 // words behind `index`: one 19-instruction batch per iteration serves every group of the warp at once.
 // wrap() completes the generation when `index` reaches 624.  A whole warp (kGroup == 32: 624 is not a
 // multiple of the batch) keeps the bulk twist.
@@ -210,12 +210,30 @@ struct GroupMt19937 {
         state[first + lane] = values[lane];
 #endif
   }
-  // Regenerates the full batches among the consumed words; call it where the warp is converged.
+  // Regenerates a full batch of consumed words if there is one (two for four-lane groups: a path
+  // iteration draws six words or so).  EVERY lane of the warp must call it together: the batch is
+  // predicated, not branched, so that the barrier between its loads and its stores is the plain
+  // full-warp one (a __syncwarp on a group's mask is emulated by a loop over the warp's masks).
+  // What it leaves behind, wrap() completes.
   PT_HD void advance() {
     if (kGroup < 32) {
-      while (index - regen >= kGroup) {
-        twistBatch(regen);
-        regen += kGroup;
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+      for (int batch = 0; batch < (kGroup >= 8 ? 1 : 8 / kGroup); ++batch) {
+        const bool due = index - regen >= kGroup;
+#ifdef __CUDA_ARCH__
+        const int i = regen + static_cast<int>(glane);
+        const uint32_t value = due ? twistedWord(state, i) : 0u;
+        __syncwarp();
+        if (due)
+          state[i] = value;
+        __syncwarp();
+#else
+        if (due)
+          twistBatch(regen);
+#endif
+        regen += due ? kGroup : 0;
       }
     }
   }
