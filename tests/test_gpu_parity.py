@@ -147,12 +147,16 @@ LANE_GROUP_CASES = [
     ("multi-sphere", 24, 18, 7, 4, {}),
     ("suzanne", 16, 12, 3, 2, {}),
     ("ce", 8, 6, 2, 7, {}),
+    # radiance() at the deepest level discards 6 x 121 words per hit: more than one mt19937 generation
+    ("cornell", 8, 6, 5, 3, dict(first_u=11, first_v=11, max_depth=1)),
+    ("cornell", 8, 6, 3, 3, dict(first_u=11, first_v=7, max_depth=2)),
+    ("cornell", 8, 6, 3, 3, dict(max_depth=0)),  # camera draws only
 ]
 
 
 @pytest.mark.parametrize("lanes", [4, 8, 16, 32])
 @pytest.mark.parametrize("mode_name", ["sequential", "oo"])
-@pytest.mark.parametrize("case", LANE_GROUP_CASES, ids=lambda c: f"{c[0]}-{c[3]}passes-{len(c[5])}{c[5].get('max_depth', '')}")
+@pytest.mark.parametrize("case", LANE_GROUP_CASES, ids=lambda c: f"{c[0]}-{c[3]}passes-{len(c[5])}{c[5].get('max_depth', '')}{c[5].get('first_u', '')}")
 def test_sequential_lane_groups_match_oracle(case, mode_name, lanes, scenes, oracle, capi):
     name, w, h, spp, seed, kw = case
     mode, oracle_mode = ((capi.RNG_MT19937_SEQUENTIAL, oracle.RNG_MT19937_SEQUENTIAL) if mode_name == "sequential"
