@@ -607,8 +607,8 @@ __global__ void __launch_bounds__(kWarps * 32)
   V3 colour = mk(0, 0, 0);
   int depth = 0;
   int subPath = 0;
-  // The camera ray's surface waits in shared memory while the sample's sub-paths are traced: every lane
-  // of the group stores the same bytes and reads back what it stored itself, so no barrier is needed.
+  // The camera ray's surface waits in shared memory while the sample's sub-paths are traced: written by
+  // the group's first lane once per sample, read by all of them at every sub-path's first bounce.
   Surface &primary = primarySlots[warp * kPassesPerWarp + groupInWarp];
   bool primarySpecular = false;
   V3 acc = mk(0, 0, 0);
@@ -647,6 +647,7 @@ __global__ void __launch_bounds__(kWarps * 32)
     // The warp's groups are together here: they twist their consumed words, sweep and take the group
     // minimum side by side; a group between two pixels (maxDepth <= 0) or past its last one idles.
     const bool casting = !(finished || sampleDone);
+    __syncwarp(); // last iteration's reads of the shared slots precede this one's writes
     rng.advance();
     Nearest best{inf, 0.0, kNoPrim};
     if (casting)
@@ -682,7 +683,9 @@ __global__ void __launch_bounds__(kWarps * 32)
         surface.reflectivity = hitReflectivity(mat, hit, direction);
         hitBasis(scene, hit, surface.basisX, surface.basisY);
         if (depth == 0) {
-          primary = surface;
+          if (glane == 0)
+            primary = surface;
+          __syncwarp(mask);
           acc = mk(0, 0, 0);
           subPath = 0;
         }
