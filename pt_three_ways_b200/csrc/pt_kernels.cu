@@ -5,8 +5,9 @@
 //                           dod::Scene::render + radiance + intersect, Scene.cpp:115-254);
 //                           its kWay = 1 instantiation renders the reference's `fp` way instead:
 //                           one mt19937 per (pass, pixel), src/fp/Render.cpp:76-135
-//   renderSequentialKernel  one pass per WARP, the reference's own mt19937 stream walked in
-//                           row-major order (Scene.cpp:208-220), primitives spread over lanes
+//   renderSequentialKernel  one pass per WARP or per group of 16 / 8 / 4 lanes, the reference's own
+//                           mt19937 stream walked in row-major order (Scene.cpp:208-220), primitives
+//                           spread over the group's lanes
 //   reducePassesKernel      per-pixel accumulation of per-pass samples IN PASS ORDER
 //                           (SampledPixel::accumulate, SampledPixel.cpp:3-6)
 //   buildFilterKernel       FP32 copies + per-triangle error bounds for the stage-0 sweep

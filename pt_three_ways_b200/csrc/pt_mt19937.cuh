@@ -1,3 +1,6 @@
+// Two std::mt19937 engines: LaneMt19937 (one per lane, the `fp` way) and, at the end of the file,
+// GroupMt19937 (one per pass, shared by the lanes that walk the pass: the exact-stream policies).
+//
 // std::mt19937 for ONE LANE, for the reference's `fp` way, which seeds a fresh engine per
 // (pass, pixel) (src/fp/Render.cpp:125-126) and then draws at most a few hundred words from it.
 //
