@@ -83,9 +83,10 @@ __device__ __forceinline__ void sweepSpheres(const double4 *__restrict__ spheres
     determinant = ieeeSqrt(determinant);
     const double minusT = b - determinant;
     const double plusT = b + determinant;
-    if (minusT < kEpsilon && plusT < kEpsilon)
+    const double epsilon = PT_EPSILON;
+    if (minusT < epsilon && plusT < epsilon)
       continue;
-    const double t = minusT > kEpsilon ? minusT : plusT;
+    const double t = minusT > epsilon ? minusT : plusT;
     if (t < best.t) {
       best.t = t;
       best.prim = -(i + 1);
@@ -108,8 +109,9 @@ __device__ __forceinline__ void testTriangle(V3 v0, V3 e1, V3 e2, V3 o, V3 d, in
   const double v = dot(d, qVec) * invDet;
   const double t = dot(e2, qVec) * invDet;
   // `continue` conditions of Scene.cpp:67,89 and the acceptance test of :94, as one predicate.
-  const bool reject = (fabs(det) < kEpsilon) | (u < 0.0) | (u > 1.0) | (v < 0.0) | (u + v > 1);
-  const bool accept = !reject & (kFpWay ? t >= kEpsilon : t > kEpsilon) & (t < best.t);
+  const double epsilon = PT_EPSILON; // (from the constant bank: one load instead of two moves per trip)
+  const bool reject = (fabs(det) < epsilon) | (u < 0.0) | (u > 1.0) | (v < 0.0) | (u + v > 1);
+  const bool accept = !reject & (kFpWay ? t >= epsilon : t > epsilon) & (t < best.t);
   if (accept) {
     best.t = t;
     best.det = det;

@@ -36,14 +36,39 @@ __device__ __forceinline__ V3 cross(V3 a, V3 b) {
             fma(a.x, b.y, -(a.y * b.x)));
 }
 // Correctly rounded sqrt and division expand to ~50 SASS instructions each (MUFU seed, Newton
-// steps, exponent fix-ups).  Everywhere except the innermost triangle loop they are called
-// out of line: same IEEE results, but the megakernel's code stays inside the instruction cache.
-static __device__ __noinline__ double ieeeSqrt(double x) { return sqrt(x); }
-static __device__ __noinline__ double ieeeDiv(double a, double b) { return a / b; }
-static __device__ __noinline__ double ieeeRcpSqrt(double x) { return 1.0 / sqrt(x); }
+// steps, exponent fix-ups).  In the one-kernel forms (pt_kernels.cu) they are called out of line
+// everywhere except the innermost triangle loop: same IEEE results, but the megakernel's code stays
+// inside the instruction cache.  PT_INLINE_LEVEL (set by the including .cu file) inlines 1: these,
+// 2: + the sin/cos pair, 3: + Philox, 4: + cone sampling; the three-kernel pipeline uses 3.
+#ifndef PT_INLINE_LEVEL
+#define PT_INLINE_LEVEL 0
+#endif
+#if PT_INLINE_LEVEL >= 1
+#define PT_IEEE_ATTR __forceinline__
+#else
+#define PT_IEEE_ATTR __noinline__
+#endif
+#if PT_INLINE_LEVEL >= 2
+#define PT_SINCOS_ATTR __forceinline__
+#else
+#define PT_SINCOS_ATTR __noinline__
+#endif
+#if PT_INLINE_LEVEL >= 3
+#define PT_PHILOX_ATTR __forceinline__
+#else
+#define PT_PHILOX_ATTR __noinline__
+#endif
+#if PT_INLINE_LEVEL >= 4
+#define PT_CONE_ATTR __forceinline__
+#else
+#define PT_CONE_ATTR __noinline__
+#endif
+static __device__ PT_IEEE_ATTR double ieeeSqrt(double x) { return sqrt(x); }
+static __device__ PT_IEEE_ATTR double ieeeDiv(double a, double b) { return a / b; }
+static __device__ PT_IEEE_ATTR double ieeeRcpSqrt(double x) { return 1.0 / sqrt(x); }
 // Two independent square roots in one call: the same correctly rounded results, two Newton chains
 // to interleave (hemisphereSample's sqrt(v) and sqrt(1 - v), Samples.cpp:23,28).
-static __device__ __noinline__ double2 ieeeSqrtPair(double a, double b) { return make_double2(sqrt(a), sqrt(b)); }
+static __device__ PT_IEEE_ATTR double2 ieeeSqrtPair(double a, double b) { return make_double2(sqrt(a), sqrt(b)); }
 
 // Vec3::normalised (src/math/Vec3.impl.h:5-7): *this / length(), and operator/ multiplies by
 // the reciprocal (src/math/Vec3.h:51-54).
@@ -60,33 +85,59 @@ __device__ __forceinline__ V3 positionAlong(V3 o, V3 d, double t) {
 // Arguments on this path are bounded (angles in [-pi, 2*pi], acos on [0, 1)), so a
 // two-constant quadrant reduction and the classic double-precision polynomial kernels
 // suffice (< 1 ulp typical).  ~30 FP64 instructions for a sin/cos pair.
-__device__ __forceinline__ double kernelSin(double r) {
+//
+// A binary64 literal costs two move instructions every time it is materialised (FP64 instructions
+// take no 64-bit immediates): 30 moves per sin/cos pair, 6.7 % of the sub-path kernel's issue slots
+// on constants altogether (profiles/r2t).  Read from the constant bank, sixteen of them arrive in
+// eight LDCU.128 and feed DFMA from uniform registers.  The same literals, so the same bits.
+#ifndef PT_CONSTANTS_IN_BANK
+#define PT_CONSTANTS_IN_BANK 1
+#endif
+#define PT_SINCOS_CONSTANTS                                                                        \
+  1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,             \
+      -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,        \
+      -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,        \
+      2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,         \
+      6.36619772367581382433e-01, 1.57079632673412561417e+00, 6.07710050650619224932e-11, 0.0
+#if PT_CONSTANTS_IN_BANK
+static __constant__ __align__(16) double kSinCos[16] = {PT_SINCOS_CONSTANTS};
+static __constant__ double kEpsilonBank = 0.000000001; // kEpsilon for the loops that would rematerialise it per trip
+#define PT_EPSILON kEpsilonBank
+#else
+#define PT_EPSILON kEpsilon
+#endif
+__device__ __forceinline__ double kernelSin(double r, const double *c) { // c: six coefficients
   const double z = r * r;
-  double p = fma(1.58969099521155010221e-10, z, -2.50507602534068634195e-08);
-  p = fma(p, z, 2.75573137070700676789e-06);
-  p = fma(p, z, -1.98412698298579493134e-04);
-  p = fma(p, z, 8.33333333332248946124e-03);
-  p = fma(p, z, -1.66666666666666324348e-01);
+  double p = fma(c[0], z, c[1]);
+  p = fma(p, z, c[2]);
+  p = fma(p, z, c[3]);
+  p = fma(p, z, c[4]);
+  p = fma(p, z, c[5]);
   return fma(r * z, p, r);
 }
-__device__ __forceinline__ double kernelCos(double r) {
+__device__ __forceinline__ double kernelCos(double r, const double *c) {
   const double z = r * r;
-  double p = fma(-1.13596475577881948265e-11, z, 2.08757232129817482790e-09);
-  p = fma(p, z, -2.75573143513906633035e-07);
-  p = fma(p, z, 2.48015872894767294178e-05);
-  p = fma(p, z, -1.38888888888741095749e-03);
-  p = fma(p, z, 4.16666666666666019037e-02);
+  double p = fma(c[0], z, c[1]);
+  p = fma(p, z, c[2]);
+  p = fma(p, z, c[3]);
+  p = fma(p, z, c[4]);
+  p = fma(p, z, c[5]);
   return fma(z * z, p, fma(-0.5, z, 1.0));
 }
 // Out of line (one copy for every caller), results returned BY VALUE: reference parameters of a
 // non-inlined function travel through local memory.
-static __device__ __noinline__ double2 sinCosPair(double x) { // {sin x, cos x}
-  const double kd = rint(x * 6.36619772367581382433e-01); // round half to even
+static __device__ PT_SINCOS_ATTR double2 sinCosPair(double x) { // {sin x, cos x}
+#if PT_CONSTANTS_IN_BANK
+  const double *c = kSinCos;
+#else
+  const double c[16] = {PT_SINCOS_CONSTANTS};
+#endif
+  const double kd = rint(x * c[12]); // 2/pi; round half to even
   const int k = static_cast<int>(kd);
-  double r = fma(-kd, 1.57079632673412561417e+00, x);
-  r = fma(-kd, 6.07710050650619224932e-11, r);
-  const double sr = kernelSin(r);
-  const double cr = kernelCos(r);
+  double r = fma(-kd, c[13], x);     // pi/2, high part
+  r = fma(-kd, c[14], r);            // pi/2, low part
+  const double sr = kernelSin(r, c);
+  const double cr = kernelCos(r, c + 6);
   const double a = (k & 1) ? cr : sr;
   const double b = (k & 1) ? sr : cr;
   return make_double2((k & 2) ? -a : a, ((k + 1) & 2) ? -b : b);
@@ -137,7 +188,7 @@ struct Philox4 {
 };
 constexpr uint32_t kPhiloxKeyHigh = 0xB200D0D0u;
 // Philox4x32-10 (Salmon et al., SC'11): counter (c0..c3), key (k0,k1).
-static __device__ __noinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+static __device__ PT_PHILOX_ATTR Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
                                                       uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int round = 0; round < 10; ++round) {
@@ -160,7 +211,7 @@ static __device__ __noinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, u
 struct Philox8 {
   uint32_t w[8];
 };
-static __device__ __noinline__ Philox8 philox4x32_10_pair(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0,
+static __device__ PT_PHILOX_ATTR Philox8 philox4x32_10_pair(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0,
                                                            uint32_t k1) {
   uint32_t a0 = c0, a1 = c1, a2 = c2, a3 = 0u, b0 = c0, b1 = c1, b2 = c2, b3 = 1u;
 #pragma unroll
@@ -223,7 +274,7 @@ __device__ __forceinline__ V3 transform(const Basis &b, V3 p) {
 }
 // coneSample (src/math/Samples.cpp:6-19).  Rare (specular picks only): kept out of line so the
 // hot loop's instruction footprint stays inside the instruction cache.
-static __device__ __noinline__ V3 coneSample(V3 direction, double coneTheta, double u, double v) {
+static __device__ PT_CONE_ATTR V3 coneSample(V3 direction, double coneTheta, double u, double v) {
   if (coneTheta < kEpsilon)
     return direction;
   coneTheta = coneTheta * (1.0 - ieeeDiv(2.0 * arcCos(u), kPi));
@@ -238,7 +289,7 @@ static __device__ __noinline__ V3 coneSample(V3 direction, double coneTheta, dou
 // normalised(basis.transform(cos(t)*r, sin(t)*r, z)), which has the same shape as
 // hemisphereSample()'s and is therefore executed once, by specular and diffuse lanes together,
 // in the megakernel.  Returns true when the cone is degenerate and `direction` is the answer.
-static __device__ __noinline__ bool coneSampleSetup(V3 direction, double coneTheta, double u, double v,
+static __device__ PT_CONE_ATTR bool coneSampleSetup(V3 direction, double coneTheta, double u, double v,
                                                     Basis &basis, double &randomTheta, double &radius,
                                                     double &zScale) {
   if (coneTheta < kEpsilon)

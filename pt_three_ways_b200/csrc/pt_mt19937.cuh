@@ -220,7 +220,7 @@ struct GroupMt19937 {
   // What it leaves behind, wrap() completes.
   PT_HD void advance() {
     if (kGroup < 32) {
-#ifdef __CUDACC__
+#ifdef __CUDA_ARCH__
 #pragma unroll
 #endif
       for (int batch = 0; batch < (kGroup >= 8 ? 1 : 8 / kGroup); ++batch) {

@@ -1,9 +1,31 @@
 #!/bin/bash
-# Two-GPU session: multi-device parity with the final kernels (the sequential policies share the passes
-# out between devices, each device picks its own lanes per pass) and the 2-rank bench line.
+# Scratch A/B: how much of the out-of-line arithmetic to inline.  L = level in the three-kernel pipeline
+# (1 IEEE sqrt/div, 2 + sin/cos, 3 + Philox, 4 + cone sampling), K = the same in pt_kernels.cu
+# (fp-way megakernel, exact-stream kernel).
 OUT=gpurun_out
 mkdir -p $OUT
-echo "== multi-device parity"; timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_fp_way.py -m gpu -q 2>&1 | tail -3 | tee $OUT/r2u_multi_tests.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29602 \
-    bench.py --gpus 2 --steps 5 --warmup 3 > $OUT/scale_n2_r2u.json 2> $OUT/scale_n2_r2u.err
-head -c 400 $OUT/scale_n2_r2u.json; echo; tail -2 $OUT/scale_n2_r2u.err | cut -c1-300
+cp pt_three_ways_b200/libptb200.so /tmp/libptb200_keep.so
+for v in L1K0 L2K0 L3K0 L4K0; do
+  cp pt_three_ways_b200/variants/libptb200_$v.so pt_three_ways_b200/libptb200.so
+  echo "== variant $v"
+  SWEEP_CONFIGS=128 SWEEP_SEQUENTIAL=0 timeout 300 python tools/sweep_configs.py cornell 640 480 64 2>&1 | cut -c1-140
+  SWEEP_CONFIGS=217 SWEEP_SEQUENTIAL=0 timeout 300 python tools/sweep_configs.py suzanne 640 480 16 2>&1 | cut -c1-140
+  SWEEP_CONFIGS=217 SWEEP_SEQUENTIAL=0 timeout 300 python tools/sweep_configs.py ce 1280 720 2 2>&1 | cut -c1-140
+done 2>&1 | tee $OUT/r2y_inline_ab.txt
+for v in L1K0 L1K1 L1K2; do
+  cp pt_three_ways_b200/variants/libptb200_$v.so pt_three_ways_b200/libptb200.so
+  echo "== variant $v (pt_kernels.cu)"
+  timeout 300 python tools/sequential_rates.py cornell 160 120 4096 0 2>&1 | cut -c1-150
+  timeout 300 python - <<'PY'
+import sys; sys.path.insert(0, ".")
+from pt_three_ways_b200 import capi, scenefile
+scene = scenefile.load("tests/golden/scenes/cornell.ptscene")
+ctx = capi.Context(0); ctx.upload_scene(scene)
+cam = scene.camera(640, 480); params = capi.make_params(640, 480, spp=64, seed=1)
+opts = capi.make_options(rng_mode=capi.RNG_MT19937_PER_PIXEL)
+ctx.render(cam, params, opts)
+best = min(ctx.render(cam, params, opts)["sweep_kernel_ms"] for _ in range(3))
+print("fp way Msamples/s", 640 * 480 * 64 / best / 1e3)
+PY
+done 2>&1 | tee -a $OUT/r2y_inline_ab.txt
+cp /tmp/libptb200_keep.so pt_three_ways_b200/libptb200.so
