@@ -19,8 +19,6 @@
 //
 // Results are bit-identical to the one-kernel form (and to the oracle): the same arithmetic in
 // the same order, only distributed differently over lanes.
-#include "pt_kernels.h"
-
 // The arithmetic helpers that the one-kernel forms call out of line (correctly rounded sqrt / division,
 // the sin/cos pair, Philox) are INLINED here: the sub-path kernel's hot loop is small enough for the
 // instruction cache, and a call costs its argument / result moves and a scheduling barrier — 230.2 ->
@@ -28,8 +26,10 @@
 // session (profiles/r2y_inline_ab.txt); the fp-way megakernel and the exact-stream kernel are faster
 // with the calls (pt_kernels.cu keeps level 0), cone sampling is rare and stays out of line.
 #ifndef PT_INLINE_LEVEL
-#define PT_INLINE_LEVEL 3
+#define PT_INLINE_LEVEL 3 // (before the first header that pulls in pt_math.cuh)
 #endif
+#include "pt_kernels.h"
+
 #include "pt_device.cuh"
 #include "pt_stage.cuh"
 
