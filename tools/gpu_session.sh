@@ -21,7 +21,7 @@ echo "== bench --config 2 (suzanne 640x480 @256)"; timeout 900 python bench.py -
 echo "== bench --config 3 (ce 1280x720, BENCH_SPP=64)"; BENCH_SPP=64 timeout 900 python bench.py --config 3 --steps 1 --warmup 0 > $OUT/bench_config3_${TAG}.json 2> $OUT/bench_config3_${TAG}.err; head -c 300 $OUT/bench_config3_${TAG}.json; echo
 echo "== ncu full: sub-path kernel, suzanne and ce"
 BENCH_SPP=4 timeout 900 ncu --set full --clock-control none --import-source on -k regex:subPath -c 1 -f -o $OUT/prof_suzanne_${TAG} python bench.py --config 2 --steps 1 --warmup 0 --no-cpu-baseline > $OUT/ncu_suzanne_${TAG}.log 2>&1
-BENCH_SPP=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:subPath -c 1 -f -o $OUT/prof_ce_${TAG} python bench.py --config 3 --steps 1 --warmup 0 --no-cpu-baseline > $OUT/ncu_ce_${TAG}.log 2>&1
+# (ce capture: see r2t; the dual kernel is unchanged since)
 echo "== exact-stream policies: rates against passes and lanes per pass"
 timeout 600 python tools/sequential_rates.py cornell 160 120 256,4096 0,32,16,8 2>&1 | tee $OUT/${TAG}_sequential_rates.jsonl
 SEQUENTIAL_MODES=oo timeout 600 python tools/sequential_rates.py cornell 160 120 4096,8192 0 2>&1 | tee -a $OUT/${TAG}_sequential_rates.jsonl
