@@ -82,6 +82,12 @@ def test_argument_validation_precedes_device_use(capi, scenes):
     with pytest.raises(capi.Ptb200Error) as err:
         capi.render(scene, cam, capi.make_params(8, 6), capi.make_options(rng_mode=4))
     assert err.value.code == 1 and "unknown rngMode" in str(err.value)
+    for lanes in (1, 5, 64, -8):
+        with pytest.raises(capi.Ptb200Error) as err:
+            capi.render(scene, cam, capi.make_params(8, 6),
+                        capi.make_options(rng_mode=capi.RNG_MT19937_SEQUENTIAL, lanes_per_pass=lanes))
+        assert err.value.code == 1 and "lanesPerPass" in str(err.value)
+    assert capi.PtRenderOptions.lanesPerPass.offset == 24  # the first of the two formerly reserved words
 
 
 def test_product_does_not_touch_the_oracle():
