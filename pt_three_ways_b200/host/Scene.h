@@ -132,6 +132,8 @@ public:
   // Render on exactly these CUDA ordinals (row-partitioned framebuffer, ptb200_render_multi).
   void setDevices(std::vector<int32_t> devices) { deviceList_ = std::move(devices); useAllDevices_ = false; }
   void setPassesPerBatch(int passes) { options_.passesPerBatch = passes; }
+  // Exact-stream policies: lanes that share one pass (4, 8, 16, 32; 0 = chosen from the pass count).
+  void setLanesPerPass(int lanes) { options_.lanesPerPass = lanes; }
   [[nodiscard]] const PtStats &lastStats() const noexcept { return lastStats_; }
   [[nodiscard]] size_t numTriangles() const noexcept { return triangleMaterial_.size(); }
   [[nodiscard]] size_t numSpheres() const noexcept { return sphereMaterial_.size(); }

@@ -93,10 +93,11 @@ int usage(const char *argv0) {
             << " [-w W] [-h H] [--spp N] [--max-cpus N] [--first-bounce-u N] [--first-bounce-v N]\n"
                "       [--max-depth N] [--seed N] [--preview] [--save-every SECS] [--way dod|fp|oo]\n"
                "       [--scene NAME] [--raw] [--rng keyed|exact] [--gpus N] [--device K]\n"
-               "       [--scenes DIR] [--ptscene FILE] <output>\n"
+               "       [--lanes-per-pass 0|4|8|16|32] [--scenes DIR] [--ptscene FILE] <output>\n"
                "       --merge <a.raw> <b.raw>... [--raw] <output>   (sum framebuffers instead of rendering)\n"
                "  --way dod (the default here; the reference's default is oo) renders the dod estimator with\n"
-               "  --rng keyed (default) or exact; --gpus N uses devices [--device, --device + N), 0 = all.\n";
+               "  --rng keyed (default) or exact; --gpus N uses devices [--device, --device + N), 0 = all;\n"
+               "  --lanes-per-pass: how many lanes share a pass of the exact stream (0 = chosen from --spp).\n";
   return 1;
 }
 
@@ -108,6 +109,7 @@ int main(int argc, const char *argv[]) {
   int saveEvery = 30;
   int gpus = 1;
   int device = 0;
+  int lanesPerPass = 0;
   std::string way = "dod";
   std::string sceneName = "cornell";
   std::string scenesDir = "scenes";
@@ -141,6 +143,7 @@ int main(int argc, const char *argv[]) {
     else if (arg == "--rng") rng = value();
     else if (arg == "--gpus") gpus = std::stoi(value());
     else if (arg == "--device") device = std::stoi(value());
+    else if (arg == "--lanes-per-pass") lanesPerPass = std::stoi(value());
     else if (arg == "--scenes") scenesDir = value();
     else if (arg == "--ptscene") ptsceneFile = value();
     else if (arg == "--merge") {
@@ -236,6 +239,7 @@ int main(int argc, const char *argv[]) {
                      : way == "oo" ? PTB200_RNG_MT19937_SEQUENTIAL_OO
                      : rng == "exact" ? PTB200_RNG_MT19937_SEQUENTIAL : PTB200_RNG_KEYED_PHILOX);
     scene.setDevice(device);
+    scene.setLanesPerPass(lanesPerPass);
     if (gpus == 0) { // every visible device
       scene.setUseAllDevices(true);
     } else if (gpus > 1) { // devices [device, device + gpus)
